@@ -1,0 +1,2 @@
+/* cvshim: everything the reference needs lives in opencv2/core.hpp (test infrastructure, see there). */
+#include <opencv2/core.hpp>
