@@ -1,0 +1,493 @@
+// api.cu -- the C ABI of include/sift_b200.h: handle, workspace layout, stage orchestration.
+//
+// One handle = one device workspace for up to max_batch frames of up to max_rows x max_cols.  The whole path
+// (base blur -> 5 x octave blur+DoG -> extrema+refine -> orientation -> order+scan -> descriptors) is ten
+// kernel launches per chunk of max_batch frames, all asynchronous on the caller's stream, no host sync and no
+// CPU fallback anywhere: if CUDA is unavailable every entry point returns SIFT_B200_ERR_CUDA.
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "sift_internal.cuh"
+
+using namespace siftb200;
+
+namespace {
+thread_local std::string g_err;
+int fail(int code, const std::string& msg) { g_err = msg; return code; }
+#define CUDA_TRY(expr)                                                                                  \
+    do {                                                                                                \
+        cudaError_t e_ = (expr);                                                                        \
+        if (e_ != cudaSuccess) return fail(SIFT_B200_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+
+int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+int round_up(int v, int m) { return (v + m - 1) / m * m; }
+}  // namespace
+
+struct SiftB200 {
+    int device = 0, max_rows = 0, max_cols = 0, max_batch = 0, cap_kp = 0;
+    cudaStream_t stream = nullptr;
+    float* ws = nullptr;        // fused-pipeline levels: 7 per octave (G0..G2, D0..D3) x max_batch frames
+    size_t ws_floats = 0;
+    float* ws_full = nullptr;   // stage-level API: 9 levels per octave, one frame (lazy)
+    size_t ws_full_floats = 0;
+    DetectBuf db{};
+    float* d_img = nullptr;     // staging for host entry points [max_batch][max_rows*max_cols]
+    SiftKeypoint* d_kp = nullptr;
+    float* d_desc = nullptr;
+    int* d_counts = nullptr;
+    int* h_counts = nullptr;    // pinned
+    long long launches = 0;
+    bool stage_timing = false;
+    cudaEvent_t ev[8] = {};
+    bool ev_valid = false;
+};
+
+namespace {
+
+size_t frame_floats(int rows, int cols, int n_oct, int levels) {
+    size_t n = 0;
+    for (int o = 0; o < n_oct; ++o) {
+        n += (size_t)round_up(cols, 32) * rows * levels;
+        rows /= 2; cols /= 2;
+    }
+    return n;
+}
+
+// Lay the levels of every octave out in `base`: [level][frame][rows_o][pitch_o].
+int make_view(float* base, int rows, int cols, int n_oct, int n_frames, bool full, PyrView* pv) {
+    if (n_oct < 1 || n_oct > kMaxOctaves) return SIFT_B200_ERR_ARG;
+    memset(pv, 0, sizeof(*pv));
+    pv->n_oct = n_oct;
+    int tiles = 0;
+    float* p = base;
+    for (int o = 0; o < n_oct; ++o) {
+        if (rows < 1 || cols < 1) return SIFT_B200_ERR_TOO_SMALL;
+        OctaveView& v = pv->oct[o];
+        v.rows = rows; v.cols = cols; v.pitch = round_up(cols, 32);
+        v.frame_stride = (size_t)v.pitch * rows;
+        const size_t lvl = v.frame_stride * n_frames;
+        for (int i = 0; i < kNumScales; ++i) {
+            if (i < 3 || full) { v.G[i] = p; p += lvl; } else v.G[i] = nullptr;
+        }
+        for (int i = 0; i < kNumScales - 1; ++i) { v.D[i] = p; p += lvl; }
+        // extrema strips: 30 x 16 outputs over the interior [5, rows-5) x [5, cols-5)  (detect.cu)
+        const int in_c = cols - 2 * kImgBorder, in_r = rows - 2 * kImgBorder;
+        v.tiles_x = in_c > 0 ? (in_c + 29) / 30 : 0;
+        v.tile_base = tiles;
+        tiles += (in_c > 0 && in_r > 0) ? v.tiles_x * ((in_r + 15) / 16) : 0;
+        rows /= 2; cols /= 2;
+    }
+    pv->total_tiles = tiles;
+    return SIFT_B200_OK;
+}
+
+// 1-D factor of the reference's 2-D tap K[i][j]/8192 = exp(-(i^2+j^2)/den)/(2 PI s^2), den = float(2*s*s)
+// (src/sift.cpp:95-108): exp(-i^2/den)/sqrt(2 PI s^2), computed in double and rounded to float once.
+int make_taps(float sigma, float* taps /* >= 2*radius+1 */, int max_radius) {
+    const float t3 = 3 * sigma;
+    const int w = (int)floor((double)t3);
+    if (w > max_radius) return -1;
+    const float den_f = 2 * sigma * sigma;
+    const double PI = 3.14159265359;
+    const double norm = sqrt(1. / (2 * PI * sigma * sigma));
+    for (int i = -w; i <= w; ++i) taps[i + w] = (float)(norm * exp(-(double)(i * i) / (double)den_f));
+    return w;
+}
+
+void pipeline_sigmas(float sig[5]) {
+    const double Sigma = 1.6, k = pow(2.0, 1.0 / kOctaveLayers);
+    sig[0] = (float)sqrt(Sigma * Sigma + 0.2 * 0.2);  // base (src/sift.cpp:237)
+    for (int i = 1; i < kNumScales; ++i) {
+        const double st = pow(k * 1.0, (double)i) * Sigma;
+        sig[i] = (float)sqrt(st * st - Sigma * Sigma);  // src/sift.cpp:240-245
+    }
+}
+
+int ensure_full(SiftB200* h, int rows, int cols, int n_oct) {
+    const size_t need = frame_floats(rows, cols, n_oct, 9);
+    if (need > h->ws_full_floats) {
+        if (h->ws_full) cudaFree(h->ws_full);
+        h->ws_full = nullptr; h->ws_full_floats = 0;
+        CUDA_TRY(cudaMalloc((void**)&h->ws_full, need * sizeof(float)));
+        h->ws_full_floats = need;
+    }
+    return SIFT_B200_OK;
+}
+
+int check_dims(const SiftB200* h, int rows, int cols) {
+    if (!h) return fail(SIFT_B200_ERR_ARG, "null handle");
+    if (rows < 1 || cols < 1 || rows > h->max_rows || cols > h->max_cols || rows >= 8192 || cols >= 8192)
+        return fail(SIFT_B200_ERR_ARG, "image size outside the handle's max_rows x max_cols (or >= 8192)");
+    return SIFT_B200_OK;
+}
+
+// upload / download one packed level set (dense rows) <-> pitched workspace levels of frame 0
+int copy_levels(const PyrView& pv, bool gauss, int per, float* packed, bool to_device, cudaStream_t st) {
+    for (int o = 0; o < pv.n_oct; ++o) {
+        const OctaveView& v = pv.oct[o];
+        for (int i = 0; i < per; ++i) {
+            float* lv = gauss ? v.G[i] : v.D[i];
+            if (to_device) CUDA_TRY(cudaMemcpy2DAsync(lv, (size_t)v.pitch * 4, packed, (size_t)v.cols * 4, (size_t)v.cols * 4, v.rows, cudaMemcpyHostToDevice, st));
+            else CUDA_TRY(cudaMemcpy2DAsync(packed, (size_t)v.cols * 4, lv, (size_t)v.pitch * 4, (size_t)v.cols * 4, v.rows, cudaMemcpyDeviceToHost, st));
+            packed += (size_t)v.rows * v.cols;
+        }
+    }
+    return SIFT_B200_OK;
+}
+
+int run_pipeline(SiftB200* h, const float* d_imgs, const uint8_t* d_imgs8, int n_frames, int rows, int cols, SiftKeypoint* d_kp, float* d_desc,
+                 int* d_counts, int cap, cudaStream_t st) {
+    int rc = check_dims(h, rows, cols);
+    if (rc) return rc;
+    if (n_frames < 0 || cap < 1 || cap > h->cap_kp) return fail(SIFT_B200_ERR_ARG, "cap must be in [1, max_kp_per_frame]");
+    if ((rows >> 4) < 1 || (cols >> 4) < 1) return fail(SIFT_B200_ERR_TOO_SMALL, "image smaller than 16 px: octave 4 would be empty (reference throws in cv::resize)");
+    CUDA_TRY(cudaSetDevice(h->device));
+    const int n_oct = 5;  // SIFT_NCL hard-codes 5 octaves (src/sift.cpp:67-68,78)
+    for (int f0 = 0; f0 < n_frames; f0 += h->max_batch) {
+        const int nf = n_frames - f0 < h->max_batch ? n_frames - f0 : h->max_batch;
+        PyrView pv;
+        rc = make_view(h->ws, rows, cols, n_oct, nf, false, &pv);
+        if (rc) return fail(rc, "make_view");
+        const bool timing = h->stage_timing && f0 + nf >= n_frames;
+        if (timing) cudaEventRecord(h->ev[0], st);
+        const size_t fs = (size_t)rows * cols;
+        h->launches += launch_base_blur(d_imgs ? d_imgs + f0 * fs : nullptr, fs, cols, d_imgs8 ? d_imgs8 + f0 * fs : nullptr, pv.oct[0], nf, st);
+        if (timing) cudaEventRecord(h->ev[1], st);
+        for (int o = 0; o < n_oct; ++o) h->launches += launch_octave(pv, o, nf, false, st);
+        if (timing) cudaEventRecord(h->ev[2], st);
+        h->launches += launch_extrema(pv, h->db, nf, st);
+        if (timing) cudaEventRecord(h->ev[3], st);
+        h->launches += launch_orientation(pv, h->db, nf, st);
+        if (timing) cudaEventRecord(h->ev[4], st);
+        h->launches += launch_order_scan(h->db, nf, d_counts + f0, st);
+        if (timing) cudaEventRecord(h->ev[5], st);
+        h->launches += launch_describe(pv, h->db, nf, d_kp + (size_t)f0 * cap, d_desc + (size_t)f0 * cap * 128, cap, st);
+        if (timing) { cudaEventRecord(h->ev[6], st); h->ev_valid = true; }
+    }
+    CUDA_TRY(cudaGetLastError());
+    return SIFT_B200_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* sift_b200_last_error(void) { return g_err.c_str(); }
+const char* sift_b200_version(void) { return "sift_b200 0.1 (sm_100a)"; }
+
+int sift_b200_create(SiftB200** out, int max_rows, int max_cols, int max_batch, int max_kp_per_frame, int device) {
+    if (!out || max_rows < 16 || max_cols < 16 || max_rows >= 8192 || max_cols >= 8192 || max_batch < 1 || max_kp_per_frame < 1)
+        return fail(SIFT_B200_ERR_ARG, "sift_b200_create: bad argument (16 <= rows, cols < 8192; batch, cap >= 1)");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) return fail(SIFT_B200_ERR_CUDA, "no CUDA device: this library has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail(SIFT_B200_ERR_ARG, "bad device ordinal");
+    CUDA_TRY(cudaSetDevice(device));
+    SiftB200* h = new SiftB200();
+    h->device = device; h->max_rows = max_rows; h->max_cols = max_cols; h->max_batch = max_batch; h->cap_kp = max_kp_per_frame;
+    *out = h;
+    CUDA_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    h->ws_floats = frame_floats(max_rows, max_cols, 5, 7) * max_batch;
+    CUDA_TRY(cudaMalloc((void**)&h->ws, h->ws_floats * sizeof(float)));
+    DetectBuf& db = h->db;
+    db.cap_r = max_kp_per_frame;
+    db.cap_r_pow2 = next_pow2(db.cap_r);
+    const size_t F = max_batch, C = db.cap_r;
+    CUDA_TRY(cudaMalloc((void**)&db.refined, F * C * sizeof(Refined)));
+    CUDA_TRY(cudaMalloc((void**)&db.n_refined, F * sizeof(int)));
+    CUDA_TRY(cudaMalloc((void**)&db.angles, F * C * kMaxPeaks * sizeof(float)));
+    CUDA_TRY(cudaMalloc((void**)&db.n_peaks, F * C * sizeof(int)));
+    CUDA_TRY(cudaMalloc((void**)&db.order, F * C * sizeof(int)));
+    CUDA_TRY(cudaMalloc((void**)&db.kp_offset, F * C * sizeof(int)));
+    CUDA_TRY(cudaMalloc((void**)&db.sort_tmp, F * (size_t)db.cap_r_pow2 * sizeof(unsigned long long)));
+    CUDA_TRY(cudaMalloc((void**)&h->d_counts, F * sizeof(int)));
+    CUDA_TRY(cudaMallocHost((void**)&h->h_counts, F * sizeof(int)));
+    for (auto& e : h->ev) CUDA_TRY(cudaEventCreate(&e));
+    float sig[5];
+    pipeline_sigmas(sig);
+    float taps[5][kTapStride];
+    memset(taps, 0, sizeof(taps));
+    for (int s = 0; s < 5; ++s)
+        if (make_taps(sig[s], taps[s], kMaxRadius) < 0) return fail(SIFT_B200_ERR_ARG, "tap radius");
+    upload_taps(taps);
+    init_pyramid_kernels();
+    init_detect_kernels();
+    init_describe_kernels();
+    CUDA_TRY(cudaGetLastError());
+    return SIFT_B200_OK;
+}
+
+int sift_b200_destroy(SiftB200* h) {
+    if (!h) return SIFT_B200_OK;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    cudaFree(h->ws); cudaFree(h->ws_full);
+    cudaFree(h->db.refined); cudaFree(h->db.n_refined); cudaFree(h->db.angles); cudaFree(h->db.n_peaks);
+    cudaFree(h->db.order); cudaFree(h->db.kp_offset); cudaFree(h->db.sort_tmp);
+    cudaFree(h->d_img); cudaFree(h->d_kp); cudaFree(h->d_desc); cudaFree(h->d_counts);
+    cudaFreeHost(h->h_counts);
+    for (auto& e : h->ev) if (e) cudaEventDestroy(e);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return SIFT_B200_OK;
+}
+
+int sift_b200_detect_describe_batch_dev(SiftB200* h, const float* d_imgs, int n_frames, int rows, int cols, SiftKeypoint* d_kp, float* d_desc,
+                                        int* d_counts, int cap, void* stream) {
+    if (!d_imgs || !d_kp || !d_desc || !d_counts) return fail(SIFT_B200_ERR_ARG, "null buffer");
+    return run_pipeline(h, d_imgs, nullptr, n_frames, rows, cols, d_kp, d_desc, d_counts, cap, (cudaStream_t)stream);
+}
+
+int sift_b200_detect_describe_batch_dev_u8(SiftB200* h, const uint8_t* d_imgs, int n_frames, int rows, int cols, SiftKeypoint* d_kp, float* d_desc,
+                                           int* d_counts, int cap, void* stream) {
+    if (!d_imgs || !d_kp || !d_desc || !d_counts) return fail(SIFT_B200_ERR_ARG, "null buffer");
+    return run_pipeline(h, nullptr, d_imgs, n_frames, rows, cols, d_kp, d_desc, d_counts, cap, (cudaStream_t)stream);
+}
+
+static int ensure_staging(SiftB200* h) {
+    if (h->d_img) return SIFT_B200_OK;
+    const size_t F = h->max_batch;
+    CUDA_TRY(cudaMalloc((void**)&h->d_img, F * (size_t)h->max_rows * h->max_cols * sizeof(float)));
+    CUDA_TRY(cudaMalloc((void**)&h->d_kp, F * (size_t)h->cap_kp * sizeof(SiftKeypoint)));
+    CUDA_TRY(cudaMalloc((void**)&h->d_desc, F * (size_t)h->cap_kp * 128 * sizeof(float)));
+    return SIFT_B200_OK;
+}
+
+int sift_b200_detect_describe_batch_host(SiftB200* h, const float* imgs, int n_frames, int rows, int cols, SiftKeypoint* kp_out, float* desc_out,
+                                         int* counts_out, int cap) {
+    int rc = check_dims(h, rows, cols);
+    if (rc) return rc;
+    if (!imgs || !kp_out || !desc_out || !counts_out) return fail(SIFT_B200_ERR_ARG, "null buffer");
+    CUDA_TRY(cudaSetDevice(h->device));
+    if ((rc = ensure_staging(h))) return rc;
+    const size_t fs = (size_t)rows * cols;
+    int status = SIFT_B200_OK;
+    for (int f0 = 0; f0 < n_frames; f0 += h->max_batch) {
+        const int nf = n_frames - f0 < h->max_batch ? n_frames - f0 : h->max_batch;
+        CUDA_TRY(cudaMemcpyAsync(h->d_img, imgs + f0 * fs, nf * fs * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+        rc = run_pipeline(h, h->d_img, nullptr, nf, rows, cols, h->d_kp, h->d_desc, h->d_counts, cap, h->stream);
+        if (rc) return rc;
+        CUDA_TRY(cudaMemcpyAsync(h->h_counts, h->d_counts, nf * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+        for (int f = 0; f < nf; ++f) {
+            int n = h->h_counts[f];
+            counts_out[f0 + f] = n;
+            if (n > cap) { n = cap; status = SIFT_B200_ERR_CAPACITY; }
+            if (n > 0) {
+                CUDA_TRY(cudaMemcpyAsync(kp_out + (size_t)(f0 + f) * cap, h->d_kp + (size_t)f * cap, n * sizeof(SiftKeypoint), cudaMemcpyDeviceToHost, h->stream));
+                CUDA_TRY(cudaMemcpyAsync(desc_out + (size_t)(f0 + f) * cap * 128, h->d_desc + (size_t)f * cap * 128, (size_t)n * 128 * sizeof(float),
+                                         cudaMemcpyDeviceToHost, h->stream));
+            }
+        }
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+    }
+    if (status) g_err = "keypoint capacity exceeded: outputs truncated";
+    return status;
+}
+
+int sift_b200_detect_describe(SiftB200* h, const float* img, int rows, int cols, size_t row_stride_bytes, SiftKeypoint* kp_out, float* desc_out, int cap,
+                              int* n_out) {
+    int rc = check_dims(h, rows, cols);
+    if (rc) return rc;
+    if (!img || !kp_out || !desc_out || !n_out) return fail(SIFT_B200_ERR_ARG, "null buffer");
+    if (row_stride_bytes == 0) row_stride_bytes = (size_t)cols * 4;
+    if (row_stride_bytes < (size_t)cols * 4) return fail(SIFT_B200_ERR_ARG, "row stride smaller than a row");
+    CUDA_TRY(cudaSetDevice(h->device));
+    if ((rc = ensure_staging(h))) return rc;
+    CUDA_TRY(cudaMemcpy2DAsync(h->d_img, (size_t)cols * 4, img, row_stride_bytes, (size_t)cols * 4, rows, cudaMemcpyHostToDevice, h->stream));
+    rc = run_pipeline(h, h->d_img, nullptr, 1, rows, cols, h->d_kp, h->d_desc, h->d_counts, cap, h->stream);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(h->h_counts, h->d_counts, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    int n = h->h_counts[0];
+    *n_out = n;
+    int status = SIFT_B200_OK;
+    if (n > cap) { n = cap; status = fail(SIFT_B200_ERR_CAPACITY, "keypoint capacity exceeded: outputs truncated"); }
+    if (n > 0) {
+        CUDA_TRY(cudaMemcpyAsync(kp_out, h->d_kp, n * sizeof(SiftKeypoint), cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(cudaMemcpyAsync(desc_out, h->d_desc, (size_t)n * 128 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+    }
+    return status;
+}
+
+// ---- sub-modules --------------------------------------------------------------------------------------------
+
+static int blur_any(SiftB200* h, const float* src, int rows, int cols, double sigma_d, float* dst, bool one_d) {
+    if (!h || !src || !dst || rows < 1 || cols < 1) return fail(SIFT_B200_ERR_ARG, "bad argument");
+    CUDA_TRY(cudaSetDevice(h->device));
+    std::vector<float> taps;
+    int radius, hi;
+    if (!one_d) {
+        const float sigma = (float)sigma_d;  // Gaussian_Blur passes sigma through a float parameter (src/sift.cpp:95,128)
+        const float t3 = 3 * sigma;
+        radius = (int)floor((double)t3);
+        if (radius < 0 || radius > 4096) return fail(SIFT_B200_ERR_ARG, "sigma out of range");
+        taps.resize(2 * radius + 1);
+        make_taps(sigma, taps.data(), radius);
+        hi = radius;
+    } else {  // getGaussianKernel1D keeps sigma in double; the tap loop is k in [-w, w) (src/sift.cpp:157-168,196)
+        radius = (int)floor(3 * sigma_d);
+        if (radius < 0 || radius > 4096) return fail(SIFT_B200_ERR_ARG, "sigma out of range");
+        taps.resize(2 * radius + 1);
+        const double PI = 3.14159265359;
+        for (int i = -radius; i <= radius; ++i) taps[i + radius] = (float)(1. / sqrt(2 * PI * sigma_d * sigma_d) * exp(-((double)i * i) * 1. / (2 * sigma_d * sigma_d)));
+        hi = radius - 1;
+    }
+    float *d_src = nullptr, *d_dst = nullptr, *d_taps = nullptr;
+    const size_t n = (size_t)rows * cols;
+    CUDA_TRY(cudaMalloc((void**)&d_src, n * 4));
+    CUDA_TRY(cudaMalloc((void**)&d_dst, n * 4));
+    CUDA_TRY(cudaMalloc((void**)&d_taps, taps.size() * 4));
+    CUDA_TRY(cudaMemcpyAsync(d_src, src, n * 4, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaMemcpyAsync(d_taps, taps.data(), taps.size() * 4, cudaMemcpyHostToDevice, h->stream));
+    const int nl = launch_generic_blur(d_src, d_dst, rows, cols, d_taps, radius, hi, h->stream);
+    if (nl < 0) return fail(SIFT_B200_ERR_CUDA, "scratch allocation failed");
+    h->launches += nl;
+    CUDA_TRY(cudaMemcpyAsync(dst, d_dst, n * 4, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    cudaFree(d_src); cudaFree(d_dst); cudaFree(d_taps);
+    CUDA_TRY(cudaGetLastError());
+    return SIFT_B200_OK;
+}
+
+int sift_b200_gaussian_blur(SiftB200* h, const float* src, int rows, int cols, double sigma, float* dst) { return blur_any(h, src, rows, cols, sigma, dst, false); }
+int sift_b200_gaussian_blur_1d(SiftB200* h, const float* src, int rows, int cols, double sigma, float* dst) { return blur_any(h, src, rows, cols, sigma, dst, true); }
+
+static int check_stage(SiftB200* h, int rows, int cols, int n_oct) {
+    int rc = check_dims(h, rows, cols);
+    if (rc) return rc;
+    if (n_oct < 1 || n_oct > kMaxOctaves) return fail(SIFT_B200_ERR_ARG, "n_octaves must be in [1, 8]");
+    if ((rows >> (n_oct - 1)) < 1 || (cols >> (n_oct - 1)) < 1) return fail(SIFT_B200_ERR_TOO_SMALL, "an octave would be empty");
+    CUDA_TRY(cudaSetDevice(h->device));
+    return ensure_full(h, rows, cols, n_oct);
+}
+
+int sift_b200_build_gaussian_pyramid(SiftB200* h, const float* img, int rows, int cols, int n_octaves, float* gpyr) {
+    int rc = check_stage(h, rows, cols, n_octaves);
+    if (rc) return rc;
+    if (!img || !gpyr) return fail(SIFT_B200_ERR_ARG, "null buffer");
+    if ((rc = ensure_staging(h))) return rc;
+    PyrView pv;
+    if ((rc = make_view(h->ws_full, rows, cols, n_octaves, 1, true, &pv))) return fail(rc, "make_view");
+    CUDA_TRY(cudaMemcpyAsync(h->d_img, img, (size_t)rows * cols * 4, cudaMemcpyHostToDevice, h->stream));
+    h->launches += launch_base_blur(h->d_img, (size_t)rows * cols, cols, nullptr, pv.oct[0], 1, h->stream);
+    for (int o = 0; o < n_octaves; ++o) h->launches += launch_octave(pv, o, 1, true, h->stream);
+    if ((rc = copy_levels(pv, true, 5, gpyr, false, h->stream))) return rc;
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    CUDA_TRY(cudaGetLastError());
+    return SIFT_B200_OK;
+}
+
+int sift_b200_build_dog_pyramid(SiftB200* h, const float* gpyr, int rows, int cols, int n_octaves, float* dogpyr) {
+    int rc = check_stage(h, rows, cols, n_octaves);
+    if (rc) return rc;
+    if (!gpyr || !dogpyr) return fail(SIFT_B200_ERR_ARG, "null buffer");
+    PyrView pv;
+    if ((rc = make_view(h->ws_full, rows, cols, n_octaves, 1, true, &pv))) return fail(rc, "make_view");
+    if ((rc = copy_levels(pv, true, 5, const_cast<float*>(gpyr), true, h->stream))) return rc;
+    h->launches += launch_dog(pv, 1, h->stream);
+    if ((rc = copy_levels(pv, false, 4, dogpyr, false, h->stream))) return rc;
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    CUDA_TRY(cudaGetLastError());
+    return SIFT_B200_OK;
+}
+
+int sift_b200_find_scale_space_extrema(SiftB200* h, const float* gpyr, const float* dogpyr, int rows, int cols, int n_octaves, SiftKeypoint* kp_out, int cap,
+                                       int* n_out) {
+    int rc = check_stage(h, rows, cols, n_octaves);
+    if (rc) return rc;
+    if (!gpyr || !dogpyr || !kp_out || !n_out || cap < 1 || cap > h->cap_kp) return fail(SIFT_B200_ERR_ARG, "bad argument");
+    if ((rc = ensure_staging(h))) return rc;
+    PyrView pv;
+    if ((rc = make_view(h->ws_full, rows, cols, n_octaves, 1, true, &pv))) return fail(rc, "make_view");
+    if ((rc = copy_levels(pv, true, 5, const_cast<float*>(gpyr), true, h->stream))) return rc;
+    if ((rc = copy_levels(pv, false, 4, const_cast<float*>(dogpyr), true, h->stream))) return rc;
+    h->launches += launch_extrema(pv, h->db, 1, h->stream);
+    h->launches += launch_orientation(pv, h->db, 1, h->stream);
+    h->launches += launch_order_scan(h->db, 1, h->d_counts, h->stream);
+    // the descriptor kernel also emits the keypoint records; descriptors land in staging and are dropped
+    h->launches += launch_describe(pv, h->db, 1, h->d_kp, h->d_desc, cap, h->stream);
+    CUDA_TRY(cudaMemcpyAsync(h->h_counts, h->d_counts, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    int n = h->h_counts[0];
+    *n_out = n;
+    int status = SIFT_B200_OK;
+    if (n > cap) { n = cap; status = fail(SIFT_B200_ERR_CAPACITY, "keypoint capacity exceeded: outputs truncated"); }
+    if (n > 0) CUDA_TRY(cudaMemcpy(kp_out, h->d_kp, n * sizeof(SiftKeypoint), cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaGetLastError());
+    return status;
+}
+
+int sift_b200_cal_descriptor(SiftB200* h, const float* gpyr, int rows, int cols, int n_octaves, const SiftKeypoint* kps, int n, float* desc, int first_octave) {
+    int rc = check_stage(h, rows, cols, n_octaves);
+    if (rc) return rc;
+    if (!gpyr || n < 0 || (n > 0 && (!kps || !desc))) return fail(SIFT_B200_ERR_ARG, "bad argument");
+    if (n == 0) return SIFT_B200_OK;
+    PyrView pv;
+    if ((rc = make_view(h->ws_full, rows, cols, n_octaves, 1, true, &pv))) return fail(rc, "make_view");
+    if ((rc = copy_levels(pv, true, 5, const_cast<float*>(gpyr), true, h->stream))) return rc;
+    SiftKeypoint* d_k = nullptr; float* d_d = nullptr; int* d_err = nullptr;
+    CUDA_TRY(cudaMalloc((void**)&d_k, (size_t)n * sizeof(SiftKeypoint)));
+    CUDA_TRY(cudaMalloc((void**)&d_d, (size_t)n * 128 * 4));
+    CUDA_TRY(cudaMalloc((void**)&d_err, 4));
+    CUDA_TRY(cudaMemsetAsync(d_err, 0, 4, h->stream));
+    CUDA_TRY(cudaMemcpyAsync(d_k, kps, (size_t)n * sizeof(SiftKeypoint), cudaMemcpyHostToDevice, h->stream));
+    h->launches += launch_describe_given(pv, d_k, n, d_d, first_octave, d_err, h->stream);
+    int err = 0;
+    CUDA_TRY(cudaMemcpyAsync(desc, d_d, (size_t)n * 128 * 4, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaMemcpyAsync(&err, d_err, 4, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    cudaFree(d_k); cudaFree(d_d); cudaFree(d_err);
+    CUDA_TRY(cudaGetLastError());
+    if (err == 2) return fail(SIFT_B200_ERR_ARG, "keypoint scale too large: descriptor window radius exceeds 40 px (scl_octv > 3.8)");
+    if (err) return fail(SIFT_B200_ERR_ASSERT, "octave >= firstOctave && layer <= nOctaveLayers+2 (src/sift.cpp:744)");
+    return SIFT_B200_OK;
+}
+
+int sift_b200_match_knn2(SiftB200* h, const float* query, int nq, const float* train, int nt, int norm, double ratio, int32_t* idx_out, float* dist_out,
+                         uint8_t* good_out) {
+    if (!h || nq < 0 || nt < 0 || (nq > 0 && (!query || !idx_out || !dist_out)) || (nt > 0 && !train)) return fail(SIFT_B200_ERR_ARG, "bad argument");
+    if (norm != SIFT_B200_NORM_L1 && norm != SIFT_B200_NORM_L2) return fail(SIFT_B200_ERR_ARG, "norm must be NORM_L1 (2) or NORM_L2 (4)");
+    if (nq == 0) return SIFT_B200_OK;
+    CUDA_TRY(cudaSetDevice(h->device));
+    float *d_q = nullptr, *d_t = nullptr, *d_dist = nullptr; int32_t* d_idx = nullptr;
+    CUDA_TRY(cudaMalloc((void**)&d_q, (size_t)nq * 512));
+    CUDA_TRY(cudaMalloc((void**)&d_t, (size_t)(nt ? nt : 1) * 512));
+    CUDA_TRY(cudaMalloc((void**)&d_dist, (size_t)nq * 8));
+    CUDA_TRY(cudaMalloc((void**)&d_idx, (size_t)nq * 8));
+    CUDA_TRY(cudaMemcpyAsync(d_q, query, (size_t)nq * 512, cudaMemcpyHostToDevice, h->stream));
+    if (nt) CUDA_TRY(cudaMemcpyAsync(d_t, train, (size_t)nt * 512, cudaMemcpyHostToDevice, h->stream));
+    h->launches += launch_match(d_q, nq, d_t, nt, norm, d_dist, d_idx, h->stream);
+    CUDA_TRY(cudaMemcpyAsync(dist_out, d_dist, (size_t)nq * 8, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaMemcpyAsync(idx_out, d_idx, (size_t)nq * 8, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    cudaFree(d_q); cudaFree(d_t); cudaFree(d_dist); cudaFree(d_idx);
+    CUDA_TRY(cudaGetLastError());
+    if (good_out)  // ratio test exactly as written in the driver: float distance vs double product (src/main.cpp:38)
+        for (int i = 0; i < nq; ++i) good_out[i] = (idx_out[2 * i + 1] >= 0 && dist_out[2 * i] <= ratio * dist_out[2 * i + 1]) ? 1 : 0;
+    return SIFT_B200_OK;
+}
+
+long long sift_b200_launch_count(const SiftB200* h) { return h ? h->launches : 0; }
+
+int sift_b200_set_stage_timing(SiftB200* h, int on) {
+    if (!h) return fail(SIFT_B200_ERR_ARG, "null handle");
+    h->stage_timing = on != 0;
+    h->ev_valid = false;
+    return SIFT_B200_OK;
+}
+
+int sift_b200_get_stage_ms(SiftB200* h, float* ms7) {
+    if (!h || !ms7 || !h->ev_valid) return fail(SIFT_B200_ERR_ARG, "no stage timing recorded");
+    CUDA_TRY(cudaEventSynchronize(h->ev[6]));
+    for (int i = 0; i < 6; ++i) CUDA_TRY(cudaEventElapsedTime(&ms7[i], h->ev[i], h->ev[i + 1]));
+    CUDA_TRY(cudaEventElapsedTime(&ms7[6], h->ev[0], h->ev[6]));
+    return SIFT_B200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,288 @@
+// describe.cu -- 4x4x8 SIFT descriptor with the reference's RootSIFT-of-quantised tail.
+//
+// Replaces calDescriptor / unpackOctave / calcSIFTDescriptor (reference src/sift.cpp:579-753).
+// Compiled with --fmad=false so the sample arithmetic (rotation, bins, trilinear weights) rounds like the
+// CPU expression order.
+//
+// The reference scatters every window sample into a (4+2)x(4+2)x(8+2) histogram.  A scatter needs shared-memory
+// float atomics, which on sm_100a are CAS loops (ATOMS.CAST.SPIN) that serialise badly because neighbouring
+// samples hit the same bins.  So the kernel is an atomics-free, deterministic two-phase gather, one CTA (128
+// threads) per keypoint:
+//   phase 1  every window position (raster order, coalesced row loads of the Gaussian level) is evaluated ONCE:
+//            gradient, fastAtan2, magnitude, Gaussian weight -> shared staging {mag*w, obin} (0 when rejected);
+//   phase 2  thread = (cell of the 4x4 grid, row slot): walks the rows of its cell's support (|rbin-a|<1,
+//            |cbin-b|<1, a rotated square; per row the j-interval comes from the two slab inequalities) and
+//            accumulates its trilinear share into a thread-private 9-bin orientation histogram in shared memory
+//            (layout [bin][thread]: conflict-free, plain read-modify-write);
+//   tail     128 threads = 128 output elements: sum the 8 row-slot partials, fold the circular bin, then
+//            L2 -> clamp 0.2 -> x512 -> uchar (round half even) -> L1 -> sqrt with block reductions.
+// Only the inner 4x4 cells are kept by the reference (:676-684), so the border cells are never formed.
+#include "sift_internal.cuh"
+
+namespace siftb200 {
+namespace {
+
+constexpr int DW = 4, DB = 8;  // SIFT_DESCR_WIDTH, SIFT_DESCR_HIST_BINS (src/sift.cpp:12,15)
+constexpr int DT = 128;        // threads per CTA = output elements
+constexpr int MAXR = 40;       // radius = cvRound(3*scl*sqrt2*2.5), scl_octv < 3.81  
+constexpr int MAXW = 2 * MAXR + 1;
+constexpr int SLOTS = DT / 16; // row slots per cell
+constexpr int DESC_SMEM_FLOATS = 2 * MAXW * MAXW + (DB + 1) * DT + 8;
+constexpr int DESC_SMEM_BYTES = DESC_SMEM_FLOATS * 4;
+
+__device__ __forceinline__ int cv_round(float v) { return __float2int_rn(v); }
+__device__ __forceinline__ int cv_floor(float v) { return __float2int_rd(v); }
+
+__device__ __forceinline__ float fast_atan2_deg(float y, float x) {
+    const float s = (float)(180.0 / 3.1415926535897932384626433832795);
+    const float p1 = 0.9997878412794807f * s, p3 = -0.3258083974640975f * s, p5 = 0.1555786518463281f * s, p7 = -0.04432655554792128f * s;
+    const float ax = fabsf(x), ay = fabsf(y);
+    float a, c, c2;
+    if (ax >= ay) {
+        c = ay / (ax + (float)2.2204460492503131e-16);
+        c2 = c * c;
+        a = (((p7 * c2 + p5) * c2 + p3) * c2 + p1) * c;
+    } else {
+        c = ax / (ay + (float)2.2204460492503131e-16);
+        c2 = c * c;
+        a = 90.f - (((p7 * c2 + p5) * c2 + p3) * c2 + p1) * c;
+    }
+    if (x < 0) a = 180.f - a;
+    if (y < 0) a = 360.f - a;
+    return a;
+}
+
+// sum over the CTA (4 warps); every thread gets the result.  `red` = 4 floats of shared scratch.
+__device__ __forceinline__ float block_sum(float v, float* red, int tid) {
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+    __syncthreads();
+    if ((tid & 31) == 0) red[tid >> 5] = v;
+    __syncthreads();
+    return (red[0] + red[1]) + (red[2] + red[3]);
+}
+
+// calcSIFTDescriptor, src/sift.cpp:579-722, for one keypoint by one CTA.  dst: 128 floats in global memory.
+__device__ void calc_descriptor(const float* __restrict__ img, int rows, int cols, int pitch, float ptx, float pty, float ori, float scl,
+                                float* __restrict__ smem, float* __restrict__ dst) {
+    const int tid = threadIdx.x;
+    const int px = cv_round(ptx), py = cv_round(pty);
+    float cos_t = cosf(ori * (float)(3.1415926535897932384626433832795 / 180));
+    float sin_t = sinf(ori * (float)(3.1415926535897932384626433832795 / 180));
+    const float bins_per_rad = DB / 360.f;
+    const float exp_scale = -1.f / (DW * DW * 0.5f);
+    const float hist_width = 3.f * scl;
+    int radius = cv_round(hist_width * 1.4142135623730951f * (DW + 1) * 0.5f);
+    const int diag = (int)sqrt(((double)cols) * cols + ((double)rows) * rows);
+    radius = min(radius, diag);
+    radius = min(radius, MAXR);  // never binds for keypoints produced by this pipeline (scl_octv < 3.81)
+    cos_t /= hist_width;
+    sin_t /= hist_width;
+    const int w = 2 * radius + 1;
+    float* s_mag = smem;
+    float* s_ob = smem + MAXW * MAXW;
+    float* s_priv = smem + 2 * MAXW * MAXW;  // [DB+1][DT]
+    float* s_red = s_priv + (DB + 1) * DT;
+
+    // ---- phase 1: evaluate every window sample once (warp = window row, lanes = consecutive columns) ----
+    for (int i = -radius + (tid >> 5); i <= radius; i += DT / 32) {
+        const int r = py + i;
+        const bool row_ok = r > 0 && r < rows - 1;
+        const float* rowp = img + (size_t)r * pitch;
+        for (int j = -radius + (tid & 31); j <= radius; j += 32) {
+            const float c_rot = j * cos_t - i * sin_t;
+            const float r_rot = j * sin_t + i * cos_t;
+            const float rbin = r_rot + DW / 2 - 0.5f;
+            const float cbin = c_rot + DW / 2 - 0.5f;
+            const int c = px + j;
+            float mw = 0.f, ob = 0.f;
+            if (row_ok && rbin > -1 && rbin < DW && cbin > -1 && cbin < DW && c > 0 && c < cols - 1) {
+                const float* q = rowp + c;
+                const float dx = __ldg(q + 1) - __ldg(q - 1);
+                const float dy = __ldg(q - pitch) - __ldg(q + pitch);
+                const float o_ = fast_atan2_deg(dy, dx);
+                const float m_ = sqrtf(dx * dx + dy * dy);
+                const float w_ = expf((c_rot * c_rot + r_rot * r_rot) * exp_scale);
+                ob = (o_ - ori) * bins_per_rad;
+                mw = m_ * w_;
+            }
+            const int idx = (i + radius) * w + (j + radius);
+            s_mag[idx] = mw;
+            s_ob[idx] = ob;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k <= DB; ++k) s_priv[k * DT + tid] = 0.f;
+    __syncthreads();
+
+    // ---- phase 2: gather.  thread = (cell, row slot) ----
+    {
+        const int cell = tid & 15, slot = tid >> 4;
+        const int a = cell >> 2, b = cell & 3;
+        // cell centre in pixel offsets: rbin = a, cbin = b  <=>  r_rot = a-1.5, c_rot = b-1.5 (units of hist_width)
+        const float ct = cos_t * hist_width, st = sin_t * hist_width;  // ~cos, sin
+        const float rr = (a - 1.5f) * hist_width, cr = (b - 1.5f) * hist_width;
+        const float ic = -cr * st + rr * ct;
+        const float ext = hist_width * (fabsf(ct) + fabsf(st)) + 1.5f;
+        int ilo = max(-radius, (int)ceilf(ic - ext));
+        int ihi = min(radius, (int)floorf(ic + ext));
+        ilo = max(ilo, 1 - py);
+        ihi = min(ihi, rows - 2 - py);
+        const float inv_s = fabsf(sin_t) > 1e-6f ? 1.f / sin_t : 0.f;
+        const float inv_c = fabsf(cos_t) > 1e-6f ? 1.f / cos_t : 0.f;
+        float* priv = s_priv + tid;
+        for (int i = ilo + slot; i <= ihi; i += SLOTS) {
+            // a-1 <= rbin < a+1 with rbin = j*sin_t + i*cos_t + 1.5 ;  b-1 <= cbin < b+1 with cbin = j*cos_t - i*sin_t + 1.5
+            float lo = (float)-radius, hi = (float)radius;
+            if (inv_s != 0.f) {
+                const float u0 = (a - 2.5f - i * cos_t) * inv_s, u1 = (a - 0.5f - i * cos_t) * inv_s;
+                lo = fmaxf(lo, fminf(u0, u1));
+                hi = fminf(hi, fmaxf(u0, u1));
+            }
+            if (inv_c != 0.f) {
+                const float u0 = (b - 2.5f + i * sin_t) * inv_c, u1 = (b - 0.5f + i * sin_t) * inv_c;
+                lo = fmaxf(lo, fminf(u0, u1));
+                hi = fminf(hi, fmaxf(u0, u1));
+            }
+            int jlo = max(max(-radius, 1 - px), (int)floorf(lo) - 1);
+            int jhi = min(min(radius, cols - 2 - px), (int)ceilf(hi) + 1);
+            const int base = (i + radius) * w + radius;
+            for (int j = jlo; j <= jhi; ++j) {
+                const float c_rot = j * cos_t - i * sin_t;
+                const float r_rot = j * sin_t + i * cos_t;
+                float rbin = r_rot + DW / 2 - 0.5f;
+                float cbin = c_rot + DW / 2 - 0.5f;
+                const int r0 = cv_floor(rbin), c0 = cv_floor(cbin);
+                if ((unsigned)(a - r0) > 1u || (unsigned)(b - c0) > 1u) continue;
+                const float mag = s_mag[base + j];
+                if (mag == 0.f) continue;  // rejected sample (or zero vote): contributes +0
+                float obin = s_ob[base + j];
+                rbin -= r0;
+                cbin -= c0;
+                int o0 = cv_floor(obin);
+                obin -= o0;
+                if (o0 < 0) o0 += DB;
+                if (o0 >= DB) o0 -= DB;
+                // trilinear split in the reference's operation order (:656-662), keeping only this cell's share
+                const float v_r1 = mag * rbin;
+                const float vr = (r0 == a) ? mag - v_r1 : v_r1;
+                const float v_c1 = vr * cbin;
+                const float vrc = (c0 == b) ? vr - v_c1 : v_c1;
+                const float v1 = vrc * obin;
+                const float v0 = vrc - v1;
+                priv[o0 * DT] += v0;
+                priv[(o0 + 1) * DT] += v1;
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- tail: thread = output element (cell*8 + k) ----
+    const int e_cell = tid >> 3, e_k = tid & 7;
+    float v = 0.f;
+#pragma unroll
+    for (int g = 0; g < SLOTS; ++g) v += s_priv[e_k * DT + e_cell + 16 * g];
+    if (e_k == 0) {  // hist[idx] += hist[idx+n] (:680); hist[idx+n+1] is never written since o0 <= n-1
+        float f = 0.f;
+#pragma unroll
+        for (int g = 0; g < SLOTS; ++g) f += s_priv[DB * DT + e_cell + 16 * g];
+        v += f;
+    }
+    float nrm2 = block_sum(v * v, s_red, tid);
+    const float thr = sqrtf(nrm2) * 0.2f;
+    v = fminf(v, thr);
+    nrm2 = block_sum(v * v, s_red, tid);
+    nrm2 = 512.f / fmaxf(sqrtf(nrm2), 1.1920928955078125e-7f);
+    int u = __float2int_rn(v * nrm2);  // saturate_cast<uchar>: round half to even, clamp to 0..255
+    u = min(max(u, 0), 255);
+    v = (float)u * nrm2;
+    float nrm1 = block_sum(v, s_red, tid);
+    nrm1 = 1.f / fmaxf(nrm1, 1.1920928955078125e-7f);
+    dst[tid] = sqrtf(v * nrm1);
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(DT)
+    describe_kernel(const __grid_constant__ PyrView pv, const DetectBuf db, SiftKeypoint* __restrict__ kp_out, float* __restrict__ desc_out, int cap) {
+    extern __shared__ float smem[];
+    const int f = blockIdx.y;
+    int n = db.n_refined[f];
+    if (n > db.cap_r) n = db.cap_r;
+    for (int p = blockIdx.x; p < n; p += gridDim.x) {
+        const int i = db.order[(size_t)f * db.cap_r + p];
+        const Refined rec = db.refined[(size_t)f * db.cap_r + i];
+        const int np = db.n_peaks[(size_t)f * db.cap_r + i];
+        const int base = db.kp_offset[(size_t)f * db.cap_r + i];
+        // unpackOctave (:724-731); firstOctave = 0 in SIFT_NCL (:86)
+        const int octave = rec.octave & 255, layer = (rec.octave >> 8) & 255;
+        const float scale = 1.f / (1 << octave);
+        const OctaveView& ov = pv.oct[octave];
+        const float* img = ov.G[layer] + (size_t)f * ov.frame_stride;
+        const float size = rec.size * scale;
+        for (int k = 0; k < np; ++k) {
+            const int slot = base + k;
+            if (slot >= cap) break;
+            const float kp_angle = db.angles[((size_t)f * db.cap_r + i) * kMaxPeaks + k];
+            float angle = 360.f - kp_angle;
+            if (fabsf(angle - 360.f) < 1.1920928955078125e-7f) angle = 0.f;
+            calc_descriptor(img, ov.rows, ov.cols, ov.pitch, rec.x * scale, rec.y * scale, angle, size * 0.5f, smem, desc_out + ((size_t)f * cap + slot) * 128);
+            if (threadIdx.x == 0) {
+                SiftKeypoint kp;
+                kp.x = rec.x; kp.y = rec.y; kp.size = rec.size; kp.angle = kp_angle; kp.response = rec.response;
+                kp.octave = rec.octave; kp.class_id = -1;
+                kp_out[(size_t)f * cap + slot] = kp;
+            }
+        }
+    }
+}
+
+// calDescriptor on caller-supplied keypoints (stage-level API): any octave/layer the reference's CV_Assert admits.
+__global__ void __launch_bounds__(DT)
+    describe_given_kernel(const __grid_constant__ PyrView pv, const SiftKeypoint* __restrict__ kps, int n, float* __restrict__ desc_out, int first_octave,
+                          int* __restrict__ err) {
+    extern __shared__ float smem[];
+    for (int p = blockIdx.x; p < n; p += gridDim.x) {
+        const SiftKeypoint kp = kps[p];
+        int octave = kp.octave & 255;
+        const int layer = (kp.octave >> 8) & 255;
+        octave = octave < 128 ? octave : (-128 | octave);
+        const float scale = octave >= 0 ? 1.f / (1 << octave) : (float)(1 << -octave);
+        if (!(octave >= first_octave && layer <= kOctaveLayers + 2) || octave - first_octave >= pv.n_oct || layer >= kNumScales) {
+            if (threadIdx.x == 0) atomicExch(err, 1);  // CV_Assert, src/sift.cpp:744
+            continue;
+        }
+        const OctaveView& ov = pv.oct[octave - first_octave];
+        float angle = 360.f - kp.angle;
+        if (fabsf(angle - 360.f) < 1.1920928955078125e-7f) angle = 0.f;
+        const float size = kp.size * scale;
+        const float hw = 3.f * (size * 0.5f);
+        const int diag = (int)sqrt(((double)ov.cols) * ov.cols + ((double)ov.rows) * ov.rows);
+        if (min(cv_round(hw * 1.4142135623730951f * (DW + 1) * 0.5f), diag) > MAXR) {
+            if (threadIdx.x == 0) atomicExch(err, 2);  // window larger than this kernel's staging (scl_octv > 3.8)
+            continue;
+        }
+        calc_descriptor(ov.G[layer], ov.rows, ov.cols, ov.pitch, kp.x * scale, kp.y * scale, angle, size * 0.5f, smem, desc_out + (size_t)p * 128);
+    }
+}
+
+}  // namespace
+
+void init_describe_kernels() {
+    cudaFuncSetAttribute(describe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DESC_SMEM_BYTES);
+    cudaFuncSetAttribute(describe_given_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DESC_SMEM_BYTES);
+}
+
+int launch_describe(const PyrView& pv, const DetectBuf& db, int n_frames, SiftKeypoint* d_kp, float* d_desc, int cap, cudaStream_t st) {
+    dim3 grid(148 * 4, n_frames);
+    describe_kernel<<<grid, DT, DESC_SMEM_BYTES, st>>>(pv, db, d_kp, d_desc, cap);
+    return 1;
+}
+
+int launch_describe_given(const PyrView& pv, const SiftKeypoint* d_kps, int n, float* d_desc, int first_octave, int* d_err, cudaStream_t st) {
+    if (n <= 0) return 0;
+    int blocks = n < 148 * 4 ? n : 148 * 4;
+    describe_given_kernel<<<blocks, DT, DESC_SMEM_BYTES, st>>>(pv, d_kps, n, d_desc, first_octave, d_err);
+    return 1;
+}
+
+}  // namespace siftb200

@@ -1,0 +1,378 @@
+// detect.cu -- scale-space extrema, sub-pixel refinement, orientation assignment, canonical ordering.
+//
+// Replaces findScaleSpaceExtrema / findScaleSpaceExtremaComputer / adjustLocalExtrema / calcOrientationHist
+// (reference src/sift.cpp:287-577).  Compiled with --fmad=false: every mul/add rounds separately, in the
+// reference's expression order, so that given identical DoG/Gaussian levels the refinement arithmetic
+// matches the CPU bit for bit (only expf/exp2 differ by library).
+//
+//   extrema_kernel      warp = 30 columns x 16 rows strip (+1 halo lane each side, +1 halo row above/below).  Per row
+//                       the four DoG levels are loaded once (coalesced), the 3-wide row max/min come from two
+//                       shuffles, the 3-row column max/min from rolling registers: "val >= all 26 neighbours"
+//                       (:493-511) becomes val >= max of three 3x3 maxima, with no divergent probing.  The rare
+//                       survivors run the Taylor refinement + contrast/edge rejection inline and append a 32-byte
+//                       record through one atomic counter per frame.
+//   orientation_kernel  warp per refined point; lanes stride over the window and vote into LANE-PRIVATE 36-bin
+//                       histograms in shared memory ([bin][lane], conflict-free plain adds: shared float atomics
+//                       are CAS loops on sm_100a), summed with a rotated read; shuffle max-reduce, peak split.
+//   order_scan_kernel   CTA per frame: bitonic sort of (scan-order key, index) + exclusive scan of peak counts
+//                       => output slot of every (point, peak) in the reference's push_back order (:538).
+#include "sift_internal.cuh"
+
+namespace siftb200 {
+namespace {
+
+__device__ __forceinline__ int cv_round(float v) { return __float2int_rn(v); }  // cvRound: round half to even
+
+// hal::fastAtan2 scalar polynomial (degrees); same operations as oracle/oracle_prims.h.
+__device__ __forceinline__ float fast_atan2_deg(float y, float x) {
+    const float s = (float)(180.0 / 3.1415926535897932384626433832795);
+    const float p1 = 0.9997878412794807f * s, p3 = -0.3258083974640975f * s, p5 = 0.1555786518463281f * s, p7 = -0.04432655554792128f * s;
+    const float ax = fabsf(x), ay = fabsf(y);
+    float a, c, c2;
+    if (ax >= ay) {
+        c = ay / (ax + (float)2.2204460492503131e-16);
+        c2 = c * c;
+        a = (((p7 * c2 + p5) * c2 + p3) * c2 + p1) * c;
+    } else {
+        c = ax / (ay + (float)2.2204460492503131e-16);
+        c2 = c * c;
+        a = 90.f - (((p7 * c2 + p5) * c2 + p3) * c2 + p1) * c;
+    }
+    if (x < 0) a = 180.f - a;
+    if (y < 0) a = 360.f - a;
+    return a;
+}
+
+// Matx33f::solve(DECOMP_LU) = Cramer's rule with d = 1/det, zeros when det == 0 (OpenCV Matx_FastSolveOp<_,3,3,1>).
+__device__ __forceinline__ void solve3(const float* a, const float* b, float* x) {
+    float d = a[0] * (a[4] * a[8] - a[7] * a[5]) - a[1] * (a[3] * a[8] - a[6] * a[5]) + a[2] * (a[3] * a[7] - a[6] * a[4]);
+    if (d == 0) { x[0] = x[1] = x[2] = 0; return; }
+    d = 1 / d;
+    x[0] = d * (b[0] * (a[4] * a[8] - a[5] * a[7]) - a[1] * (b[1] * a[8] - a[5] * b[2]) + a[2] * (b[1] * a[7] - a[4] * b[2]));
+    x[1] = d * (a[0] * (b[1] * a[8] - a[5] * b[2]) - b[0] * (a[3] * a[8] - a[5] * a[6]) + a[2] * (a[3] * b[2] - b[1] * a[6]));
+    x[2] = d * (a[0] * (a[4] * b[2] - b[1] * a[7]) - a[1] * (a[3] * b[2] - b[1] * a[6]) + b[0] * (a[3] * a[7] - a[4] * a[6]));
+}
+
+struct Lv {
+    const float* p;
+    int pitch;
+    __device__ __forceinline__ float at(int r, int c) const { return __ldg(p + (size_t)r * pitch + c); }
+};
+
+// adjustLocalExtrema, src/sift.cpp:287-388.  D[0..3] = DoG levels of this octave/frame.
+__device__ bool adjust_local_extrema(const float* const* D, int rows, int cols, int pitch, int octv, int& layer, int& r, int& c, Refined& out) {
+    const float img_scale = (float)(1. / 255);
+    const float deriv_scale = img_scale * 0.5f;
+    const float second_deriv_scale = img_scale;
+    const float cross_deriv_scale = img_scale * 0.25f;
+    float xi = 0, xr = 0, xc = 0, contr = 0;
+    int i = 0;
+    for (; i < kMaxInterpSteps; i++) {
+        const Lv img{D[layer], pitch}, prev{D[layer - 1], pitch}, next{D[layer + 1], pitch};
+        float dD[3] = {(img.at(r, c + 1) - img.at(r, c - 1)) * deriv_scale, (img.at(r + 1, c) - img.at(r - 1, c)) * deriv_scale,
+                       (next.at(r, c) - prev.at(r, c)) * deriv_scale};
+        float v2 = img.at(r, c) * 2;
+        float dxx = (img.at(r, c + 1) + img.at(r, c - 1) - v2) * second_deriv_scale;
+        float dyy = (img.at(r + 1, c) + img.at(r - 1, c) - v2) * second_deriv_scale;
+        float dss = (next.at(r, c) + prev.at(r, c) - v2) * second_deriv_scale;
+        float dxy = (img.at(r + 1, c + 1) - img.at(r + 1, c - 1) - img.at(r - 1, c + 1) + img.at(r - 1, c - 1)) * cross_deriv_scale;
+        float dxs = (next.at(r, c + 1) - next.at(r, c - 1) - prev.at(r, c + 1) + prev.at(r, c - 1)) * cross_deriv_scale;
+        float dys = (next.at(r + 1, c) - next.at(r - 1, c) - prev.at(r + 1, c) + prev.at(r - 1, c)) * cross_deriv_scale;
+        float H[9] = {dxx, dxy, dxs, dxy, dyy, dys, dxs, dys, dss};
+        float X[3];
+        solve3(H, dD, X);
+        xi = -X[2]; xr = -X[1]; xc = -X[0];
+        if (fabsf(xi) < 0.5f && fabsf(xr) < 0.5f && fabsf(xc) < 0.5f) break;
+        const float big = (float)(INT_MAX / 3);
+        if (fabsf(xi) > big || fabsf(xr) > big || fabsf(xc) > big) return false;
+        c += cv_round(xc);
+        r += cv_round(xr);
+        layer += cv_round(xi);
+        if (layer < 1 || layer > kOctaveLayers || c < kImgBorder || c >= cols - kImgBorder || r < kImgBorder || r >= rows - kImgBorder) return false;
+    }
+    if (i >= kMaxInterpSteps) return false;
+    {
+        const Lv img{D[layer], pitch}, prev{D[layer - 1], pitch}, next{D[layer + 1], pitch};
+        float dD[3] = {(img.at(r, c + 1) - img.at(r, c - 1)) * deriv_scale, (img.at(r + 1, c) - img.at(r - 1, c)) * deriv_scale,
+                       (next.at(r, c) - prev.at(r, c)) * deriv_scale};
+        float t = 0;
+        t += dD[0] * xc; t += dD[1] * xr; t += dD[2] * xi;
+        contr = img.at(r, c) * img_scale + t * 0.5f;
+        if (fabsf(contr) * kOctaveLayers < 0.04f) return false;
+        float v2 = img.at(r, c) * 2.f;
+        float dxx = (img.at(r, c + 1) + img.at(r, c - 1) - v2) * second_deriv_scale;
+        float dyy = (img.at(r + 1, c) + img.at(r - 1, c) - v2) * second_deriv_scale;
+        float dxy = (img.at(r + 1, c + 1) - img.at(r + 1, c - 1) - img.at(r - 1, c + 1) + img.at(r - 1, c - 1)) * cross_deriv_scale;
+        float tr = dxx + dyy;
+        float det = dxx * dyy - dxy * dxy;
+        const float edgeThreshold = 10.f;
+        if (det <= 0 || tr * tr * edgeThreshold >= (edgeThreshold + 1) * (edgeThreshold + 1) * det) return false;
+    }
+    out.x = (c + xc) * (1 << octv);
+    out.y = (r + xr) * (1 << octv);
+    out.octave = octv + (layer << 8) + (__double2int_rn(((double)xi + 0.5) * 255) << 16);
+    // powf(2.f, y): evaluated in double and rounded once so it agrees with a correctly rounded host powf
+    out.size = 1.6f * (float)exp2((double)((layer + xi) / kOctaveLayers)) * (1 << octv) * 2;
+    out.response = fabsf(contr);
+    out.rc = ((uint32_t)r << 16) | (uint32_t)c;
+    out.pad = 0;
+    return true;
+}
+
+constexpr int EX_COLS = 30;  // output columns per warp (lanes 1..30; lanes 0 and 31 are halo)
+constexpr int EX_ROWS = 16;  // output rows per warp
+constexpr int EX_WARPS = 4;
+
+__global__ void __launch_bounds__(EX_WARPS * 32) extrema_kernel(const __grid_constant__ PyrView pv, const DetectBuf db) {
+    const int lane = threadIdx.x & 31;
+    const int strip = blockIdx.x * EX_WARPS + (threadIdx.x >> 5);
+    if (strip >= pv.total_tiles) return;
+    int o = 0;
+#pragma unroll 1
+    for (int k = 1; k < pv.n_oct; ++k)
+        if (strip >= pv.oct[k].tile_base) o = k;
+    const OctaveView& ov = pv.oct[o];
+    const int t = strip - ov.tile_base;
+    const int f = blockIdx.y;
+    const int rows = ov.rows, cols = ov.cols, pitch = ov.pitch;
+    const int c = kImgBorder + (t % ov.tiles_x) * EX_COLS - 1 + lane;
+    const int r_begin = kImgBorder + (t / ov.tiles_x) * EX_ROWS;
+    const int r_end = min(r_begin + EX_ROWS, rows - kImgBorder);  // exclusive
+    const size_t foff = (size_t)f * ov.frame_stride;
+    const float* D[4] = {ov.D[0] + foff, ov.D[1] + foff, ov.D[2] + foff, ov.D[3] + foff};
+    const bool col_in = c < cols;
+    const bool col_out = lane >= 1 && lane <= EX_COLS && c < cols - kImgBorder;
+
+    float hmaxA[4], hminA[4], hmaxB[4], hminB[4], cenB[2];
+#pragma unroll
+    for (int l = 0; l < 4; ++l) { hmaxA[l] = hmaxB[l] = -3.4e38f; hminA[l] = hminB[l] = 3.4e38f; }
+    cenB[0] = cenB[1] = 0.f;
+#pragma unroll 1
+    for (int y = r_begin - 1; y <= r_end; ++y) {
+        float hmaxC[4], hminC[4], cenC[2];
+#pragma unroll
+        for (int l = 0; l < 4; ++l) {
+            const float v = col_in ? __ldg(D[l] + (size_t)y * pitch + c) : 0.f;
+            const float vl = __shfl_up_sync(0xffffffffu, v, 1), vr = __shfl_down_sync(0xffffffffu, v, 1);
+            hmaxC[l] = fmaxf(v, fmaxf(vl, vr));
+            hminC[l] = fminf(v, fminf(vl, vr));
+            if (l == 1) cenC[0] = v;
+            if (l == 2) cenC[1] = v;
+        }
+        if (y >= r_begin + 1) {  // rows y-2, y-1, y are in flight: test row y-1
+            const int r = y - 1;
+            float M[4], m[4];
+#pragma unroll
+            for (int l = 0; l < 4; ++l) {
+                M[l] = fmaxf(hmaxA[l], fmaxf(hmaxB[l], hmaxC[l]));
+                m[l] = fminf(hminA[l], fminf(hminB[l], hminC[l]));
+            }
+#pragma unroll
+            for (int layer0 = 1; layer0 <= kOctaveLayers; ++layer0) {
+                const float val = cenB[layer0 - 1];
+                // |val| > 8 (the literal threshold, :564) and val >= / <= all 26 neighbours (non-strict, :494-511)
+                const bool hit = col_out && ((val > 8.0f && val >= fmaxf(M[layer0 - 1], fmaxf(M[layer0], M[layer0 + 1]))) ||
+                                             (val < -8.0f && val <= fminf(m[layer0 - 1], fminf(m[layer0], m[layer0 + 1]))));
+                if (hit) {
+                    int r1 = r, c1 = c, layer = layer0;
+                    Refined rec;
+                    if (adjust_local_extrema(D, rows, cols, pitch, o, layer, r1, c1, rec)) {
+                        rec.key = ((uint32_t)o << 27) | ((uint32_t)(layer0 - 1) << 26) | ((uint32_t)r << 13) | (uint32_t)c;
+                        const int slot = atomicAdd(db.n_refined + f, 1);
+                        if (slot < db.cap_r) db.refined[(size_t)f * db.cap_r + slot] = rec;
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int l = 0; l < 4; ++l) { hmaxA[l] = hmaxB[l]; hminA[l] = hminB[l]; hmaxB[l] = hmaxC[l]; hminB[l] = hminC[l]; }
+        cenB[0] = cenC[0]; cenB[1] = cenC[1];
+    }
+}
+
+// ---- orientation: calcOrientationHist + peak logic, src/sift.cpp:389-458, 518-541 ----------------------------
+constexpr int ORI_WARPS = 8;
+
+__global__ void __launch_bounds__(ORI_WARPS * 32) orientation_kernel(const __grid_constant__ PyrView pv, const DetectBuf db) {
+    __shared__ float s_tmp[ORI_WARPS][kOriBins + 4];
+    __shared__ float s_hist[ORI_WARPS][kOriBins];
+    __shared__ float s_priv[ORI_WARPS][kOriBins * 32];  // lane-private bins, [bin][lane]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int f = blockIdx.y;
+    int n = db.n_refined[f];
+    if (n > db.cap_r) n = db.cap_r;
+    float* temphist = s_tmp[warp] + 2;
+    float* hist = s_hist[warp];
+    for (int i = blockIdx.x * ORI_WARPS + warp; i < n; i += gridDim.x * ORI_WARPS) {
+        const Refined rec = db.refined[(size_t)f * db.cap_r + i];
+        const int o = rec.octave & 255, layer = (rec.octave >> 8) & 255;
+        const OctaveView& ov = pv.oct[o];
+        const float* img = ov.G[layer] + (size_t)f * ov.frame_stride;
+        const int rows = ov.rows, cols = ov.cols, pitch = ov.pitch;
+        const int py = rec.rc >> 16, px = rec.rc & 0xffff;
+        const float scl_octv = rec.size * 0.5f / (1 << o);
+        const int radius = cv_round(4.5f * scl_octv);
+        const float sigma = 1.5f * scl_octv;
+        const float expf_scale = -1.f / (2.f * sigma * sigma);
+        float* priv = s_priv[warp] + lane;
+#pragma unroll
+        for (int b = 0; b < kOriBins; ++b) priv[b * 32] = 0.f;
+        const int w = 2 * radius + 1;
+        for (int idx = lane; idx < w * w; idx += 32) {
+            const int ii = idx / w - radius, jj = idx % w - radius;
+            const int y = py + ii, x = px + jj;
+            if (y <= 0 || y >= rows - 1 || x <= 0 || x >= cols - 1) continue;
+            const float* q = img + (size_t)y * pitch + x;
+            const float dx = __ldg(q + 1) - __ldg(q - 1);
+            const float dy = __ldg(q - pitch) - __ldg(q + pitch);
+            const float wgt = expf((ii * ii + jj * jj) * expf_scale);
+            const float ori = fast_atan2_deg(dy, dx);
+            const float mag = sqrtf(dx * dx + dy * dy);
+            int bin = cv_round((kOriBins / 360.f) * ori);
+            if (bin >= kOriBins) bin -= kOriBins;
+            if (bin < 0) bin += kOriBins;
+            priv[bin * 32] += wgt * mag;
+        }
+        __syncwarp();
+        for (int b = lane; b < kOriBins; b += 32) {  // rotated read: lane b starts at copy b, all banks distinct
+            float acc = 0.f;
+#pragma unroll 8
+            for (int k = 0; k < 32; ++k) acc += s_priv[warp][b * 32 + ((k + b) & 31)];
+            temphist[b] = acc;
+        }
+        __syncwarp();
+        if (lane == 0) {
+            temphist[-1] = temphist[kOriBins - 1];
+            temphist[-2] = temphist[kOriBins - 2];
+            temphist[kOriBins] = temphist[0];
+            temphist[kOriBins + 1] = temphist[1];
+        }
+        __syncwarp();
+        float mx = -3.4e38f;
+        for (int b = lane; b < kOriBins; b += 32) {
+            const float h = (temphist[b - 2] + temphist[b + 2]) * (1.f / 16.f) + (temphist[b - 1] + temphist[b + 1]) * (4.f / 16.f) + temphist[b] * (6.f / 16.f);
+            hist[b] = h;
+            mx = fmaxf(mx, h);
+        }
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, s));
+        __syncwarp();
+        const float mag_thr = mx * 0.8f;
+        int count = 0;
+        float* ang_out = db.angles + ((size_t)f * db.cap_r + i) * kMaxPeaks;
+        for (int base = 0; base < kOriBins; base += 32) {
+            const int j = base + lane;
+            bool pk = false;
+            float angle = 0.f;
+            if (j < kOriBins) {
+                const int l = j > 0 ? j - 1 : kOriBins - 1;
+                const int r2 = j < kOriBins - 1 ? j + 1 : 0;
+                const float hj = hist[j], hl = hist[l], hr = hist[r2];
+                if (hj > hl && hj > hr && hj >= mag_thr) {
+                    float bin = j + 0.5f * (hl - hr) / (hl - 2 * hj + hr);
+                    bin = bin < 0 ? kOriBins + bin : bin >= kOriBins ? bin - kOriBins : bin;
+                    angle = 360.f - (360.f / kOriBins) * bin;
+                    if (fabsf(angle - 360.f) < 1.1920928955078125e-7f) angle = 0.f;
+                    pk = true;
+                }
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, pk);
+            if (pk) ang_out[count + __popc(m & ((1u << lane) - 1))] = angle;
+            count += __popc(m);
+        }
+        if (lane == 0) db.n_peaks[(size_t)f * db.cap_r + i] = count;
+        __syncwarp();
+    }
+}
+
+// ---- canonical order + output offsets -----------------------------------------------------------------------
+constexpr int SORT_THREADS = 1024;
+constexpr int SORT_SMEM_ELEMS = 8192;  // 64 KB of (key<<32 | index)
+
+__global__ void __launch_bounds__(SORT_THREADS) order_scan_kernel(const DetectBuf db, int* __restrict__ counts_out) {
+    extern __shared__ unsigned long long s_buf[];
+    __shared__ int s_warp[32];
+    __shared__ int s_carry;
+    const int f = blockIdx.x, tid = threadIdx.x;
+    int n = db.n_refined[f];
+    if (n > db.cap_r) n = db.cap_r;
+    int npad = 1;
+    while (npad < n) npad <<= 1;
+    unsigned long long* buf = npad <= SORT_SMEM_ELEMS ? s_buf : db.sort_tmp + (size_t)f * db.cap_r_pow2;
+    const Refined* rec = db.refined + (size_t)f * db.cap_r;
+    for (int i = tid; i < npad; i += SORT_THREADS) buf[i] = i < n ? ((unsigned long long)rec[i].key << 32) | (unsigned)i : ~0ull;
+    __syncthreads();
+    for (int k = 2; k <= npad; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = tid; i < npad; i += SORT_THREADS) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const unsigned long long a = buf[i], b = buf[ixj];
+                    const bool up = (i & k) == 0;
+                    if ((a > b) == up) { buf[i] = b; buf[ixj] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    // exclusive scan of peak counts in sorted order
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    const int* np = db.n_peaks + (size_t)f * db.cap_r;
+    int* order = db.order + (size_t)f * db.cap_r;
+    int* off = db.kp_offset + (size_t)f * db.cap_r;
+    const int lane = tid & 31, warp = tid >> 5;
+    for (int base = 0; base < n; base += SORT_THREADS) {
+        const int p = base + tid;
+        int idx = -1, v = 0;
+        if (p < n) { idx = (int)(buf[p] & 0xffffffffu); v = np[idx]; }
+        int incl = v;
+#pragma unroll
+        for (int s = 1; s < 32; s <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, s);
+            if (lane >= s) incl += t;
+        }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            int w = s_warp[lane];
+#pragma unroll
+            for (int s = 1; s < 32; s <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, w, s);
+                if (lane >= s) w += t;
+            }
+            s_warp[lane] = w;
+        }
+        __syncthreads();
+        const int carry = s_carry;
+        const int excl = carry + (warp ? s_warp[warp - 1] : 0) + incl - v;
+        if (p < n) { order[p] = idx; off[idx] = excl; }
+        __syncthreads();
+        if (tid == SORT_THREADS - 1) s_carry = carry + s_warp[31];
+        __syncthreads();
+    }
+    if (tid == 0) counts_out[f] = s_carry;
+}
+
+}  // namespace
+
+void init_detect_kernels() { cudaFuncSetAttribute(order_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SORT_SMEM_ELEMS * 8); }
+
+int launch_extrema(const PyrView& pv, const DetectBuf& db, int n_frames, cudaStream_t st) {
+    cudaMemsetAsync(db.n_refined, 0, sizeof(int) * n_frames, st);
+    dim3 grid((pv.total_tiles + EX_WARPS - 1) / EX_WARPS, n_frames);
+    extrema_kernel<<<grid, EX_WARPS * 32, 0, st>>>(pv, db);
+    return 1;
+}
+
+int launch_orientation(const PyrView& pv, const DetectBuf& db, int n_frames, cudaStream_t st) {
+    dim3 grid(64, n_frames);
+    orientation_kernel<<<grid, ORI_WARPS * 32, 0, st>>>(pv, db);
+    return 1;
+}
+
+int launch_order_scan(const DetectBuf& db, int n_frames, int* d_counts, cudaStream_t st) {
+    order_scan_kernel<<<n_frames, SORT_THREADS, SORT_SMEM_ELEMS * 8, st>>>(db, d_counts);
+    return 1;
+}
+
+}  // namespace siftb200

@@ -1,0 +1,275 @@
+// pyramid.cu -- Gaussian scale-space + DoG for sm_100a.
+//
+// Replaces Gaussian_Blur / buildGaussianPyramid / buildDoGPyramid (reference src/sift.cpp:95-153, 219-283).
+// The reference blurs every scale of an octave from the OCTAVE BASE with an unnormalised, truncated
+// (radius floor(3 sigma)) sampled 2-D Gaussian, zero padded, with source row rows-1 / col cols-1 read as
+// zero (:116).  That kernel and that mask are both separable, so each scale is two 1-D passes here.
+//
+// octave_kernel: one CTA owns a 32x64 output tile of one frame.
+//   phase 1  masked octave-base tile + 18-px halo  -> shared (coalesced 4-byte loads, odd pitch)
+//   phase 2  horizontal pass, 4 scales (radii 4/8/12/18), register-blocked: a thread produces 8 adjacent
+//            outputs of one row from 8+2r shared loads; lanes run down rows (odd pitch => conflict-free)
+//   phase 3  vertical pass, lane = column, 8 output rows per thread, all 4 scales kept in registers so the
+//            DoG subtraction, the G1/G2 stores and the NEAREST-decimated next-octave base (src[2y][2x],
+//            :253-254) are fused into the epilogue; every store is a full 128-byte row segment.
+// HBM traffic per pixel: 4 B read (+halo re-reads served by L2) and 28 B written (G1,G2,D0..D3, 1/4 G0').
+#include "sift_internal.cuh"
+
+namespace siftb200 {
+
+__constant__ float c_taps[5][kTapStride];
+
+void upload_taps(const float host_taps[5][kTapStride]) { cudaMemcpyToSymbol(c_taps, host_taps, sizeof(float) * 5 * kTapStride); }
+
+namespace {
+
+constexpr int TW = 32;   // tile width  (= warp width: one lane per column in the vertical pass)
+constexpr int TH = 64;   // tile height
+constexpr int NT = 256;  // threads per CTA
+constexpr int GRP = 8;   // outputs per thread along the filter direction
+constexpr int HP = TW + 1;  // pitch of the horizontal-pass results (odd)
+
+__host__ __device__ constexpr int rad_of(int s) { return s <= 1 ? 4 : s == 2 ? 8 : s == 3 ? 12 : 18; }
+
+// 8 outputs of a (2R+1)-tap FIR from 8+2R inputs at `in[t*stride]`; taps are compile-time constant-bank operands.
+template <int S, int STRIDE>
+__device__ __forceinline__ void fir8(const float* __restrict__ in, float (&acc)[GRP]) {
+    constexpr int R = rad_of(S);
+#pragma unroll
+    for (int k = 0; k < GRP; ++k) acc[k] = 0.f;
+#pragma unroll
+    for (int t = 0; t < GRP + 2 * R; ++t) {
+        const float v = in[t * STRIDE];
+#pragma unroll
+        for (int k = 0; k < GRP; ++k) {
+            const int j = t - k;
+            if (j >= 0 && j <= 2 * R) acc[k] = fmaf(v, c_taps[S][j], acc[k]);
+        }
+    }
+}
+
+// Horizontal pass of scale S over the rows the vertical pass will need: [HALO-R, HALO+TH+R) of the input tile.
+template <int S, int HALO>
+__device__ __forceinline__ void hpass(const float* __restrict__ sIn, float* __restrict__ sH, int tid) {
+    constexpr int R = rad_of(S);
+    constexpr int IP = TW + 2 * HALO + 1;
+    constexpr int NROWS = TH + 2 * R;
+    constexpr int NITEMS = NROWS * (TW / GRP);
+    for (int id = tid; id < NITEMS; id += NT) {
+        const int row = id % NROWS, g = id / NROWS;
+        float acc[GRP];
+        fir8<S, 1>(sIn + (HALO - R + row) * IP + (HALO - R + GRP * g), acc);
+        float* out = sH + row * HP + GRP * g;
+#pragma unroll
+        for (int k = 0; k < GRP; ++k) out[k] = acc[k];
+    }
+}
+
+template <int HALO>
+__device__ __forceinline__ void load_tile(float* __restrict__ sIn, const float* __restrict__ src, const uint8_t* __restrict__ src8, int rows,
+                                          int cols, int pitch, int ty0, int tx0, int tid) {
+    constexpr int IW = TW + 2 * HALO, IH = TH + 2 * HALO, IP = IW + 1;
+    for (int idx = tid; idx < IW * IH; idx += NT) {
+        const int y = idx / IW, x = idx - y * IW;
+        const int gy = ty0 - HALO + y, gx = tx0 - HALO + x;
+        float v = 0.f;
+        // zero padding AND the reference's ">= rows-1 / cols-1 reads as zero" window fetch (src/sift.cpp:116)
+        if (gy >= 0 && gx >= 0 && gy < rows - 1 && gx < cols - 1) v = src8 ? (float)src8[(size_t)gy * pitch + gx] : __ldg(src + (size_t)gy * pitch + gx);
+        sIn[y * IP + x] = v;
+    }
+}
+
+constexpr int H_OFF1 = 0;
+constexpr int H_OFF2 = H_OFF1 + (TH + 2 * 4) * HP;
+constexpr int H_OFF3 = H_OFF2 + (TH + 2 * 8) * HP;
+constexpr int H_OFF4 = H_OFF3 + (TH + 2 * 12) * HP;
+constexpr int H_END = H_OFF4 + (TH + 2 * 18) * HP;
+constexpr int OCT_HALO = kMaxRadius;
+constexpr int OCT_IN = (TW + 2 * OCT_HALO + 1) * (TH + 2 * OCT_HALO);
+constexpr int OCT_SMEM_BYTES = (OCT_IN + H_END) * 4;
+
+struct OctArgs {
+    const float* G0;
+    float *G1, *G2, *G3, *G4, *D0, *D1, *D2, *D3;
+    float* nextG0;
+    int rows, cols, pitch;
+    size_t frame_stride;
+    int nrows, ncols, npitch;
+    size_t nframe_stride;
+};
+
+__global__ void __launch_bounds__(NT, 3) octave_kernel(const OctArgs a) {
+    extern __shared__ float smem[];
+    float* sIn = smem;
+    float* sH = smem + OCT_IN;
+    const int tid = threadIdx.x;
+    const int tx0 = blockIdx.x * TW, ty0 = blockIdx.y * TH;
+    const size_t foff = (size_t)blockIdx.z * a.frame_stride;
+    const float* G0 = a.G0 + foff;
+
+    load_tile<OCT_HALO>(sIn, G0, nullptr, a.rows, a.cols, a.pitch, ty0, tx0, tid);
+    __syncthreads();
+    hpass<4, OCT_HALO>(sIn, sH + H_OFF4, tid);
+    hpass<3, OCT_HALO>(sIn, sH + H_OFF3, tid);
+    hpass<2, OCT_HALO>(sIn, sH + H_OFF2, tid);
+    hpass<1, OCT_HALO>(sIn, sH + H_OFF1, tid);
+    __syncthreads();
+
+    const int x = tid & 31, rg = tid >> 5;
+    float g1[GRP], g2[GRP], g3[GRP], g4[GRP];
+    fir8<1, HP>(sH + H_OFF1 + (rg * GRP) * HP + x, g1);
+    fir8<2, HP>(sH + H_OFF2 + (rg * GRP) * HP + x, g2);
+    fir8<3, HP>(sH + H_OFF3 + (rg * GRP) * HP + x, g3);
+    fir8<4, HP>(sH + H_OFF4 + (rg * GRP) * HP + x, g4);
+
+    const int gx = tx0 + x;
+    if (gx >= a.cols) return;
+    constexpr int IP = TW + 2 * OCT_HALO + 1;
+#pragma unroll
+    for (int k = 0; k < GRP; ++k) {
+        const int gy = ty0 + rg * GRP + k;
+        if (gy >= a.rows) break;
+        const size_t p = foff + (size_t)gy * a.pitch + gx;
+        // DoG level 0 uses the real base value; the masked copy in shared memory is zero on the last row/col.
+        float g0 = sIn[(OCT_HALO + rg * GRP + k) * IP + OCT_HALO + x];
+        if (gy == a.rows - 1 || gx == a.cols - 1) g0 = __ldg(a.G0 + p);
+        a.G1[p] = g1[k];
+        a.G2[p] = g2[k];
+        if (a.G3) { a.G3[p] = g3[k]; a.G4[p] = g4[k]; }
+        a.D0[p] = g1[k] - g0;
+        a.D1[p] = g2[k] - g1[k];
+        a.D2[p] = g3[k] - g2[k];
+        a.D3[p] = g4[k] - g3[k];
+        if (a.nextG0 && !((gy | gx) & 1)) {
+            const int ny = gy >> 1, nx = gx >> 1;
+            if (ny < a.nrows && nx < a.ncols) a.nextG0[(size_t)blockIdx.z * a.nframe_stride + (size_t)ny * a.npitch + nx] = g2[k];
+        }
+    }
+}
+
+// ---- base blur: image -> octave-0 base, sigma = sqrt(1.6^2 + 0.2^2), radius 4 (src/sift.cpp:237) ----------
+constexpr int BASE_HALO = 4;
+constexpr int BASE_IN = (TW + 2 * BASE_HALO + 1) * (TH + 2 * BASE_HALO);
+constexpr int BASE_SMEM_BYTES = (BASE_IN + (TH + 2 * 4) * HP) * 4;
+
+__global__ void __launch_bounds__(NT, 4)
+    base_blur_kernel(const float* __restrict__ src, const uint8_t* __restrict__ src8, size_t src_frame_stride, int src_pitch, float* __restrict__ dst,
+                     size_t dst_frame_stride, int dst_pitch, int rows, int cols) {
+    extern __shared__ float smem[];
+    float* sIn = smem;
+    float* sH = smem + BASE_IN;
+    const int tid = threadIdx.x;
+    const int tx0 = blockIdx.x * TW, ty0 = blockIdx.y * TH;
+    load_tile<BASE_HALO>(sIn, src ? src + (size_t)blockIdx.z * src_frame_stride : nullptr, src8 ? src8 + (size_t)blockIdx.z * src_frame_stride : nullptr,
+                         rows, cols, src_pitch, ty0, tx0, tid);
+    __syncthreads();
+    hpass<0, BASE_HALO>(sIn, sH, tid);
+    __syncthreads();
+    const int x = tid & 31, rg = tid >> 5;
+    float g[GRP];
+    fir8<0, HP>(sH + (rg * GRP) * HP + x, g);
+    const int gx = tx0 + x;
+    if (gx >= cols) return;
+#pragma unroll
+    for (int k = 0; k < GRP; ++k) {
+        const int gy = ty0 + rg * GRP + k;
+        if (gy >= rows) break;
+        dst[(size_t)blockIdx.z * dst_frame_stride + (size_t)gy * dst_pitch + gx] = g[k];
+    }
+}
+
+// ---- generic 1-D pass with run-time taps (stage-level Gaussian_Blur / Gaussian_Blur_1D for any sigma) ------
+// out(y,x) = sum_{k=lo..hi} taps[k-lo] * src(y+k or x+k) over source positions p with 0 <= p < limit-1
+// (the reference's mask).  Sequential accumulation in k order; `exact` rounds mul and add separately
+// (the reference's non-FMA arithmetic) so Gaussian_Blur_1D is reproduced bit for bit.
+__global__ void blur_pass_kernel(const float* __restrict__ src, float* __restrict__ dst, int rows, int cols, const float* __restrict__ taps, int lo,
+                                 int hi, int vertical, int exact, int zero_last_row) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= cols || y >= rows) return;
+    float acc = 0.f;
+    for (int k = lo; k <= hi; ++k) {
+        float v = 0.f;
+        if (vertical) {
+            const int p = y + k;
+            if (p >= 0 && p < rows - 1) v = src[(size_t)p * cols + x];
+        } else {
+            const int p = x + k;
+            if (p >= 0 && p < cols - 1 && !(zero_last_row && y >= rows - 1)) v = src[(size_t)y * cols + p];
+        }
+        const float t = taps[k - lo];
+        acc = exact ? __fadd_rn(acc, __fmul_rn(v, t)) : fmaf(v, t, acc);
+    }
+    dst[(size_t)y * cols + x] = acc;
+}
+
+__global__ void dog_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ d, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) d[i] = b[i] - a[i];
+}
+
+}  // namespace
+
+// per-device opt-in to > 48 KB dynamic shared memory; called from sift_b200_create after cudaSetDevice
+void init_pyramid_kernels() {
+    cudaFuncSetAttribute(base_blur_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BASE_SMEM_BYTES);
+    cudaFuncSetAttribute(octave_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OCT_SMEM_BYTES);
+}
+
+int launch_base_blur(const float* src, size_t src_frame_stride, int src_pitch, const uint8_t* src_u8, const OctaveView& o0, int n_frames, cudaStream_t st) {
+    dim3 grid((o0.cols + TW - 1) / TW, (o0.rows + TH - 1) / TH, n_frames);
+    base_blur_kernel<<<grid, NT, BASE_SMEM_BYTES, st>>>(src_u8 ? nullptr : src, src_u8, src_frame_stride, src_pitch, o0.G[0], o0.frame_stride, o0.pitch, o0.rows,
+                                                       o0.cols);
+    return 1;
+}
+
+int launch_octave(const PyrView& pv, int o, int n_frames, bool write_all_levels, cudaStream_t st) {
+    const OctaveView& v = pv.oct[o];
+    OctArgs a;
+    a.G0 = v.G[0]; a.G1 = v.G[1]; a.G2 = v.G[2];
+    a.G3 = write_all_levels ? v.G[3] : nullptr;
+    a.G4 = write_all_levels ? v.G[4] : nullptr;
+    a.D0 = v.D[0]; a.D1 = v.D[1]; a.D2 = v.D[2]; a.D3 = v.D[3];
+    a.rows = v.rows; a.cols = v.cols; a.pitch = v.pitch; a.frame_stride = v.frame_stride;
+    if (o + 1 < pv.n_oct) {
+        const OctaveView& n = pv.oct[o + 1];
+        a.nextG0 = n.G[0]; a.nrows = n.rows; a.ncols = n.cols; a.npitch = n.pitch; a.nframe_stride = n.frame_stride;
+    } else {
+        a.nextG0 = nullptr; a.nrows = a.ncols = a.npitch = 0; a.nframe_stride = 0;
+    }
+    dim3 grid((v.cols + TW - 1) / TW, (v.rows + TH - 1) / TH, n_frames);
+    octave_kernel<<<grid, NT, OCT_SMEM_BYTES, st>>>(a);
+    return 1;
+}
+
+// Separable blur with run-time taps: horizontal (rows >= rows-1 zeroed at the source) then vertical.
+// taps_hi: last tap offset (radius for Gaussian_Blur, radius-1 for Gaussian_Blur_1D which also runs vertical first).
+int launch_generic_blur(const float* src, float* dst, int rows, int cols, const float* d_taps, int radius, int taps_hi, cudaStream_t st) {
+    float* tmp = nullptr;
+    if (cudaMallocAsync((void**)&tmp, sizeof(float) * (size_t)rows * cols, st) != cudaSuccess) return -1;
+    dim3 blk(32, 8), grid((cols + 31) / 32, (rows + 7) / 8);
+    const bool one_d = taps_hi != radius;
+    if (!one_d) {
+        blur_pass_kernel<<<grid, blk, 0, st>>>(src, tmp, rows, cols, d_taps, -radius, taps_hi, 0, 0, 1);
+        blur_pass_kernel<<<grid, blk, 0, st>>>(tmp, dst, rows, cols, d_taps, -radius, taps_hi, 1, 0, 0);
+    } else {  // Gaussian_Blur_1D: vertical then horizontal, exact non-FMA arithmetic (src/sift.cpp:193-212)
+        blur_pass_kernel<<<grid, blk, 0, st>>>(src, tmp, rows, cols, d_taps, -radius, taps_hi, 1, 1, 0);
+        blur_pass_kernel<<<grid, blk, 0, st>>>(tmp, dst, rows, cols, d_taps, -radius, taps_hi, 0, 1, 0);
+    }
+    cudaFreeAsync(tmp, st);
+    return 2;
+}
+
+int launch_dog(const PyrView& pv, int n_frames, cudaStream_t st) {
+    int n = 0;
+    for (int o = 0; o < pv.n_oct; ++o) {
+        const OctaveView& v = pv.oct[o];
+        size_t cnt = v.frame_stride * n_frames;
+        for (int i = 0; i < kNumScales - 1; ++i) {
+            dog_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>(v.G[i], v.G[i + 1], v.D[i], cnt);
+            ++n;
+        }
+    }
+    return n;
+}
+
+}  // namespace siftb200

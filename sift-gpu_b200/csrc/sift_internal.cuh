@@ -1,0 +1,82 @@
+// sift_internal.cuh -- shared declarations of the sm_100a SIFT path (not part of the public C ABI).
+//
+// Data layout in HBM (per handle, for up to max_batch frames F):
+//   per octave o: G[0..2] (G[3..4] only for the stage-level pyramid API) and D[0..3], each
+//   [F][rows_o][pitch_o] float32 with pitch_o = cols_o rounded up to 32 floats (128-byte rows so every
+//   warp-wide row segment is a whole number of 128-byte lines).
+//   refined-point records, orientation peaks and ordering arrays: [F][cap_refined].
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/sift_b200.h"
+
+namespace siftb200 {
+
+constexpr int kMaxOctaves = 8;
+constexpr int kNumScales = 5;      // src/sift.cpp:5
+constexpr int kOctaveLayers = 2;   // src/sift.cpp:4
+constexpr int kImgBorder = 5;      // src/sift.cpp:21
+constexpr int kMaxInterpSteps = 5; // src/sift.cpp:24
+constexpr int kOriBins = 36;       // src/sift.cpp:27
+constexpr int kMaxPeaks = 18;      // strict local maxima of a 36-bin circular histogram
+constexpr int kMaxRadius = 18;     // floor(3*sig[4]) = floor(3*6.196774)
+
+struct OctaveView {
+    float* G[kNumScales];     // Gaussian levels (G[3], G[4] may be null in the fused pipeline)
+    float* D[kNumScales - 1]; // DoG levels
+    int rows, cols, pitch;    // pitch in floats
+    size_t frame_stride;      // floats between consecutive frames of one level
+    int tile_base;            // first extrema strip (30x16 outputs) of this octave in the flattened strip index
+    int tiles_x;
+};
+
+struct PyrView {
+    OctaveView oct[kMaxOctaves];
+    int n_oct;
+    int total_tiles;
+};
+
+// One record per extremum that survived adjustLocalExtrema (src/sift.cpp:287-388).
+struct Refined {
+    uint32_t key;     // scan-order key: o<<27 | (layer0-1)<<26 | r0<<13 | c0   (initial, un-refined position)
+    int32_t octave;   // packed like KeyPoint::octave
+    float x, y, size, response;
+    uint32_t rc;      // refined integer position r1<<16 | c1 in octave coordinates
+    uint32_t pad;
+};
+
+struct DetectBuf {
+    Refined* refined;    // [F][cap_r]
+    int* n_refined;      // [F]  (atomic counters, may exceed cap_r)
+    float* angles;       // [F][cap_r][kMaxPeaks]
+    int* n_peaks;        // [F][cap_r]
+    int* order;          // [F][cap_r]  sorted position -> refined index
+    int* kp_offset;      // [F][cap_r]  refined index -> first output slot
+    unsigned long long* sort_tmp; // [F][cap_r_pow2] global scratch when the frame does not fit shared memory
+    int cap_r;
+    int cap_r_pow2;
+};
+
+// Blur taps: c_taps[0] = base sigma sqrt(1.6^2+0.2^2), c_taps[1..4] = sig[1..4] (src/sift.cpp:237-245).
+// 1-D factor of the reference's 2-D kernel: exp(-i^2/den)/sqrt(2 PI sigma^2), den = float(2*sigma*sigma).
+constexpr int kTapStride = 40;
+void upload_taps(const float host_taps[5][kTapStride]);
+void init_pyramid_kernels();
+void init_detect_kernels();
+void init_describe_kernels();
+
+// ---- launchers (each returns the number of kernels it launched) ---------------------------------
+int launch_base_blur(const float* src, size_t src_frame_stride, int src_pitch, const uint8_t* src_u8, const OctaveView& o0, int n_frames,
+                     cudaStream_t st);
+int launch_octave(const PyrView& pv, int o, int n_frames, bool write_all_levels, cudaStream_t st);
+int launch_generic_blur(const float* src, float* dst, int rows, int cols, const float* d_taps, int radius, int taps_hi, cudaStream_t st);
+int launch_dog(const PyrView& pv, int n_frames, cudaStream_t st);
+int launch_extrema(const PyrView& pv, const DetectBuf& db, int n_frames, cudaStream_t st);
+int launch_orientation(const PyrView& pv, const DetectBuf& db, int n_frames, cudaStream_t st);
+int launch_order_scan(const DetectBuf& db, int n_frames, int* d_counts, cudaStream_t st);
+int launch_describe(const PyrView& pv, const DetectBuf& db, int n_frames, SiftKeypoint* d_kp, float* d_desc, int cap, cudaStream_t st);
+int launch_describe_given(const PyrView& pv, const SiftKeypoint* d_kps, int n, float* d_desc, int first_octave, int* d_err, cudaStream_t st);
+int launch_match(const float* d_q, int nq, const float* d_t, int nt, int norm, float* d_dist, int32_t* d_idx, cudaStream_t st);
+
+}  // namespace siftb200

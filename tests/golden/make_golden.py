@@ -1,0 +1,81 @@
+"""Generate the golden fixtures in tests/golden/ from oracle/_ref (the UNMODIFIED reference src/sift.cpp
+compiled against oracle/cvshim) -- run in the build container, where /root/reference exists:
+
+    python tests/golden/make_golden.py
+
+Inputs follow the reference driver (src/main.cpp:79-87): imread (BGR u8) -> optional resize to 960x960 (first CLI
+argument only, :83) -> cvtColor(COLOR_RGB2GRAY) applied to BGR data -> convertTo(CV_32FC1) without scaling.
+cv2 (the 4.13 wheel) does the decoding/colour conversion; the u8 gray image is stored so the tests never need
+/root/reference or cv2.  Everything numeric in the fixtures comes from oracle/_ref, not from the C oracle.
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as ge
+
+O = ge.load_oracle()
+from importlib import import_module
+
+ge.load_package()
+synth = import_module("sift_gpu_b200.synth")
+HERE = os.path.dirname(os.path.abspath(__file__))
+DATA = "/root/reference/data"
+
+
+def read_image(name, resized):
+    import cv2
+
+    img = cv2.imread(os.path.join(DATA, name))
+    assert img is not None
+    if resized:
+        img = cv2.resize(img, (960, 960))
+    return cv2.cvtColor(img, cv2.COLOR_RGB2GRAY)  # u8; convertTo(CV_32FC1) is a plain cast
+
+
+def main():
+    O.build()
+    ref = O.ref()
+    # 1. small synthetic frames: every intermediate of the reference (gpyr, dogpyr, keypoints, descriptors)
+    for tag, (w, h, seed) in {"synth_160x120": (160, 120, 1), "synth_odd_211x173": (211, 173, 2)}.items():
+        img = synth.recipe_s(w, h, seed=seed, blobs_per_1080p=20000)
+        g = ref.build_gaussian_pyramid(img)
+        d = ref.build_dog_pyramid(g, h, w)
+        kps = ref.find_scale_space_extrema(g, d, h, w)
+        desc = ref.cal_descriptor(g, h, w, kps)
+        k2, d2 = ref.sift_ncl(img)
+        assert k2.tobytes() == kps.tobytes() and np.array_equal(d2, desc)
+        blur1d = ref.gaussian_blur(img, 1.6, one_d=True)
+        np.savez_compressed(os.path.join(HERE, tag + ".npz"), image=img, gpyr=g.astype(np.float16 if False else np.float32), dogpyr=d, keypoints=kps,
+                            descriptors=desc, blur1d_sigma1p6=blur1d)
+        print(tag, "keypoints", len(kps))
+    # 2. config 1 / 5: data/scene.jpg as main.cpp feeds it (960x960) and data/query.jpg native
+    scene = read_image("scene.jpg", True)
+    ks, ds = ref.sift_ncl(scene.astype(np.float32))
+    np.savez_compressed(os.path.join(HERE, "scene_960.npz"), gray=scene, keypoints=ks, descriptors=ds)
+    print("scene_960 keypoints", len(ks))
+    query = read_image("query.jpg", False)
+    kq, dq = ref.sift_ncl(query.astype(np.float32))
+    print("query native keypoints", len(kq))
+    # knnMatch(query descriptors, scene descriptors) per main.cpp:25-27, cross-checked against cv2.BFMatcher below
+    import cv2
+
+    out = {}
+    for norm, cvn in ((O.NORM_L1, cv2.NORM_L1), (O.NORM_L2, cv2.NORM_L2)):
+        idx, dist, good = O.match_knn2(dq, ds, norm, 0.86)
+        m = cv2.BFMatcher(cvn).knnMatch(dq, ds, 2)
+        cv_idx = np.array([[a.trainIdx, b.trainIdx] for a, b in m], dtype=np.int32)
+        cv_dist = np.array([[a.distance, b.distance] for a, b in m], dtype=np.float32)
+        assert np.array_equal(cv_idx, idx), "oracle matcher disagrees with cv2.BFMatcher"
+        assert np.allclose(cv_dist, dist, rtol=1e-5)
+        out[f"idx_n{norm}"], out[f"dist_n{norm}"], out[f"good_n{norm}"] = idx, dist, good
+        print("norm", norm, "good matches", int(good.sum()))
+    np.savez_compressed(os.path.join(HERE, "match_query_scene.npz"), query_desc=dq, scene_desc=ds, query_kp=kq, **out)
+    np.savez_compressed(os.path.join(HERE, "query_2448.npz"), gray=query)
+
+
+if __name__ == "__main__":
+    main()
