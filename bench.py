@@ -1,0 +1,384 @@
+#!/usr/bin/env python
+"""bench.py -- SIFT 1080p frames/s (detect+describe) on N B200s, one process per GPU.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--frames B] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+A step = one pass of the whole hot path (SIFT_NCL: pyramid+DoG, extrema+refine, orientation, descriptors) over a batch
+of B synthetic 1920x1080 float32 frames per GPU (recipe S; BASELINE.json configs[1]).  Frames are
+independent, so ranks shard them with no collective on the data path (weak scaling: B frames per GPU per step).
+
+  value    frames/s with the batch already resident in HBM (CUDA events on the launching stream, max over ranks)
+  e2e      frames/s through the host-buffer C-ABI call (sift_b200_detect_describe_batch_host): pinned host frames in,
+           host keypoints/descriptors/counts out, H2D and D2H inside the timed region
+  roofline algorithmic HBM bytes / CUDA-event time for the kernel with the largest share of the step, against
+           MEASURED_PEAKS.json (per-kernel table under roofline_by_kernel; whole-path figure under roofline_pipeline)
+  cpu_baseline   the reference's CPU path timed on this box (N=1, rank 0): oracle/_ref = the unmodified src/sift.cpp
+           built against oracle/cvshim (kind "reference"), else the C oracle port
+`--impl reference` times that CPU path alone and prints the same JSON shape.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as ge  # noqa: E402
+
+ROWS, COLS = 1080, 1920
+N_OCT = 5
+METRIC = "SIFT 1080p frames/s (detect+describe)"
+WORKLOAD = "synthetic 1920x1080 grayscale float32 frames (recipe S, seeds 1234+k), SIFT_NCL detect+describe"
+
+
+# ---- workload geometry / algorithmic bytes (DESIGN.md "roofline accounting") ------------------------------
+def octave_pixels(rows=ROWS, cols=COLS, n_oct=N_OCT):
+    out = []
+    for _ in range(n_oct):
+        out.append(rows * cols)
+        rows, cols = rows // 2, cols // 2
+    return out
+
+
+def algorithmic_bytes_per_frame(n_kp: float, rows=ROWS, cols=COLS):
+    """B = 4*(P_src + 14*sumP) + 540*N bytes per frame, and its split over the kernels."""
+    P = octave_pixels(rows, cols)
+    sumP, P0 = sum(P), P[0]
+    per_kernel = {
+        "base_blur_kernel": 4 * (P0 + P0),                       # read the frame, write G0 of octave 0
+        "octave_kernel": 4 * (sumP + 6 * sumP + (sumP - P0)),    # read G0; write G1,G2,D0..D3; write the next base
+        "extrema_kernel": 4 * 4 * sumP,                          # read D0..D3 once
+        "orientation_kernel": 4 * sumP,                          # G1/G2 gathers: half of the "read G1,G2 once" term
+        "describe_kernel": 4 * sumP + 540 * n_kp,                # the other half + 28 B keypoint + 512 B descriptor
+        "order_scan_kernel": 0,
+    }
+    total = 4 * (P0 + 14 * sumP) + 540 * n_kp
+    return total, per_kernel
+
+
+# ---- helpers ---------------------------------------------------------------------------------------------
+def shard_range(n_items: int, world: int, rank: int):
+    """Contiguous block of items for `rank` (frame f -> rank f // ceil(n/world)); covers [0, n) exactly once."""
+    per = (n_items + world - 1) // world
+    lo = min(n_items, rank * per)
+    return lo, min(n_items, lo + per)
+
+
+def max_over_ranks(value: float, device=None) -> float:
+    import torch
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()):
+        return value
+    t = torch.tensor([value], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def sum_over_ranks(value: float, device=None) -> float:
+    import torch
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()):
+        return value
+    t = torch.tensor([value], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t.item())
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def make_frames(n_unique: int):
+    """n_unique recipe-S 1080p frames (seed 1234+k), cached under /tmp so repeated runs skip the numpy stamping."""
+    from importlib import import_module
+
+    ge.load_package()
+    synth = import_module("sift_gpu_b200.synth")
+    cache = f"/tmp/sift_b200_frames_{COLS}x{ROWS}_{n_unique}.npy"
+    if os.path.exists(cache):
+        try:
+            a = np.load(cache)
+            if a.shape == (n_unique, ROWS, COLS):
+                return a
+        except Exception:
+            pass
+    a = np.stack([synth.recipe_s(COLS, ROWS, seed=1234 + k) for k in range(n_unique)])
+    try:
+        np.save(cache, a)
+    except Exception:
+        pass
+    return a
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed regions."""
+
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, windows):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ts, line in self.rows:
+            if not any(a - 0.05 <= ts <= b + 0.05 for a, b in windows):
+                continue
+            parts = [p.strip() for p in line.split(",")]
+            try:
+                sm.append(float(parts[0])); smax.append(float(parts[1])); power.append(float(parts[2]))
+            except Exception:
+                continue
+            for nm, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---- reference arm: the reference's own CPU implementation ----------------------------------------------------
+def cpu_reference_run(steps: int, warmup: int, budget_s: float):
+    """Time SIFT_NCL on the CPU: oracle/_ref (unmodified src/sift.cpp, its own threading: single-threaded pyramid and
+    detection, OpenMP only in calDescriptor :738) when built, else the C oracle port with all cores."""
+    O = ge.load_oracle()
+    frame = make_frames(1)[0]
+    if O.have_ref():
+        kind, impl = "reference", O.ref()
+        cores = impl.omp_max_threads()
+        full_s = 21.0  # ~10 us per pixel on a 2-3 GHz core (direct 2-D blur, src/sift.cpp:137-149)
+        run = lambda img: impl.sift_ncl(img)
+        how = "oracle/_ref: unmodified src/sift.cpp compiled against oracle/cvshim; pyramid+detection single-threaded, calDescriptor OpenMP"
+    else:
+        kind, impl = "port", O.f32()
+        cores = os.cpu_count() or 1
+        O.set_threads(cores)
+        full_s = 3.0
+        run = lambda img: impl.sift_ncl(img)
+        how = "oracle/sift_oracle.c (C port, blur rows and descriptors OpenMP over all cores)"
+    per_step = budget_s / max(1, steps + warmup)
+    rows = int(min(ROWS, max(176, ROWS * per_step / full_s)))
+    rows -= rows % 8
+    img = np.ascontiguousarray(frame[:rows])
+    for _ in range(warmup):
+        run(img)
+    ts = []
+    n_kp = 0
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        k, _d = run(img)
+        ts.append(time.perf_counter() - t0)
+        n_kp = len(k)
+    t = float(np.mean(ts))
+    frac = rows / ROWS
+    sample = (f"{steps} x SIFT_NCL on the top {rows} of 1080 rows of the seed-1234 frame ({COLS}x{rows}, {n_kp} keypoints), "
+              f"{t:.3f} s each, scaled by rows/1080 to 1080p frames; {how}")
+    return {"value": frac / t, "unit": "frames/s", "cores": cores, "kind": kind, "sample": sample}, t
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    base, t = cpu_reference_run(args.steps, args.warmup, budget_s=150.0)
+    line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": {"workload": WORKLOAD, "note": "CPU arm: one process, host cores only, no GPU"},
+            "cpu_baseline": base, "e2e": {"value": base["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+    return 0
+
+
+# ---- our arm --------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- this framework has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    pkg = ge.load_package()
+
+    B, cap, chunk = args.frames, args.cap, args.chunk
+    uniq = make_frames(min(32, B))
+    reps = (B + len(uniq) - 1) // len(uniq)
+    host_frames = torch.from_numpy(np.concatenate([uniq] * reps)[:B]).pin_memory()
+    d_imgs = host_frames.to(dev, non_blocking=True)
+    d_kp = torch.zeros((B, cap, 28), dtype=torch.uint8, device=dev)
+    d_desc = torch.zeros((B, cap, 128), dtype=torch.float32, device=dev)
+    d_cnt = torch.zeros(B, dtype=torch.int32, device=dev)
+    h_kp = torch.zeros((B, cap, 28), dtype=torch.uint8).pin_memory()
+    h_desc = torch.zeros((B, cap, 128), dtype=torch.float32).pin_memory()
+    h_cnt = torch.zeros(B, dtype=torch.int32).pin_memory()
+    s = pkg.Sift(ROWS, COLS, max_batch=chunk, max_kp_per_frame=cap, device=local_rank)
+    stream = torch.cuda.current_stream(dev)
+    st = stream.cuda_stream
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def step_dev():
+        s.detect_describe_batch_dev(d_imgs, d_kp, d_desc, d_cnt, cap, st)
+
+    def step_host():
+        return s.detect_describe_batch_host_ptr(host_frames.data_ptr(), B, ROWS, COLS, h_kp.data_ptr(), h_desc.data_ptr(), h_cnt.data_ptr(), cap)
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    windows = []
+    # ---- device-resident throughput ----
+    for _ in range(max(3, args.warmup)):
+        step_dev()
+    barrier()
+    l0 = s.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    w0 = time.time()
+    e0.record(stream)
+    for _ in range(args.steps):
+        step_dev()
+    e1.record(stream)
+    barrier()
+    windows.append((w0, time.time()))
+    launches = s.launch_count() - l0
+    ms_step = max_over_ranks(e0.elapsed_time(e1) / args.steps, dev)
+    counts = d_cnt.cpu().numpy()
+    if (counts > cap).any():
+        raise SystemExit(f"bench.py: keypoint capacity {cap} exceeded (max count {counts.max()})")
+    frames_total = sum_over_ranks(float(B), dev)
+    value = frames_total / (ms_step * 1e-3)
+    n_kp = float(counts.mean())
+
+    # ---- per-kernel time (CUDA events between the stages of the last chunk of a step), one extra untimed step ----
+    s.set_stage_timing(True)
+    step_dev()
+    torch.cuda.synchronize(dev)
+    stage = s.stage_ms()
+    s.set_stage_timing(False)
+    last_chunk = B - ((B - 1) // chunk) * chunk
+    names = ["base_blur_kernel", "octave_kernel", "extrema_kernel", "orientation_kernel", "order_scan_kernel", "describe_kernel"]
+    peak, peak_src = load_peaks()
+    total_bytes, per_kernel_bytes = algorithmic_bytes_per_frame(n_kp)
+    by_kernel = {}
+    for nm, ms in zip(names, stage[:6]):
+        us_frame = ms * 1e3 / last_chunk
+        gbs = per_kernel_bytes[nm] / (us_frame * 1e-6) / 1e9 if us_frame > 0 else 0.0
+        by_kernel[nm] = {"us_per_frame": round(us_frame, 3), "share": round(ms / stage[6], 4), "alg_bytes_per_frame": int(per_kernel_bytes[nm]),
+                         "achieved_gbs": round(gbs, 1), "frac": round(gbs / peak, 4)}
+    top = max(names, key=lambda k: by_kernel[k]["us_per_frame"])
+    launches_of_top = {"octave_kernel": N_OCT}.get(top, 1)  # launches per chunk
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        try:
+            with open(tpath) as f:
+                traffic = json.load(f).get(top)
+        except Exception:
+            traffic = None
+    roofline = {"kernel": top, "bound": "hbm", "achieved": by_kernel[top]["achieved_gbs"], "peak": peak, "unit": "GB/s",
+                "frac": by_kernel[top]["frac"], "traffic": traffic, "peak_source": peak_src,
+                "alg_bytes_per_launch": int(per_kernel_bytes[top] * last_chunk / launches_of_top),
+                "avg_launch_us": round(by_kernel[top]["us_per_frame"] * last_chunk / launches_of_top, 2),
+                "note": "time from CUDA events around the kernel's launches inside a step (stage_ms of the C ABI); see roofline_by_kernel"}
+    pipe_gbs = (value / world) * total_bytes / 1e9
+    roofline_pipeline = {"alg_bytes_per_frame": int(total_bytes), "achieved": round(pipe_gbs, 1), "peak": peak, "unit": "GB/s",
+                         "frac": round(pipe_gbs / peak, 4), "per_gpu": True}
+
+    # ---- end to end through the host-buffer C ABI ----
+    for _ in range(2):
+        step_host()
+    barrier()
+    e_steps = max(1, min(args.steps, args.e2e_steps))
+    w0 = time.time()
+    t0 = time.perf_counter()
+    for _ in range(e_steps):
+        step_host()
+    torch.cuda.synchronize(dev)
+    t_host = (time.perf_counter() - t0) / e_steps
+    windows.append((w0, time.time()))
+    t_host = max_over_ranks(t_host, dev)
+    hc = h_cnt.numpy()
+    assert np.array_equal(hc, counts), "host and device paths disagree on keypoint counts"
+    e2e = {"value": frames_total / t_host, "unit": "frames/s", "h2d_bytes_per_step": int(B * ROWS * COLS * 4),
+           "d2h_bytes_per_step": int(hc.sum()) * 540 + 4 * B,
+           "api": "sift_b200_detect_describe_batch_host (pinned host float32 frames in; host keypoints, descriptors, counts out)"}
+    clocks = sampler.stop(windows) if sampler else None
+
+    cpu_base = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu_base, _ = cpu_reference_run(1, 0, budget_s=22.0)
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": WORKLOAD, "frames_per_step_per_gpu": B, "chunk_frames": chunk, "keypoint_capacity": cap,
+                           "mean_keypoints_per_frame": round(n_kp, 1), "parallelism": f"frame-sharded x{world}, no collectives",
+                           "l2": f"inputs larger than L2: {B} frames x 8.3 MB per step, workspace {chunk} x 77 MB"},
+                "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "roofline_by_kernel": by_kernel,
+                "roofline_pipeline": roofline_pipeline, "cpu_baseline": cpu_base}
+        print(json.dumps(line))
+    s.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--frames", type=int, default=64, help="frames per GPU per step")
+    ap.add_argument("--chunk", type=int, default=8, help="frames per internal pass (workspace size)")
+    ap.add_argument("--cap", type=int, default=6144, help="keypoint capacity per frame")
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.gpus != world and world == 1 and args.gpus > 1 and args.impl == "ours":
+        # convenience: relaunch under torchrun
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
+               "--master-port", "29517", os.path.abspath(__file__)] + sys.argv[1:]
+        return subprocess.call(cmd)
+    return run_reference(args) if args.impl == "reference" else run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,132 @@
+"""GPU tests at BASELINE.json's full sizes through size-independent properties, the batch entry points, and the
+edge cases / error behaviour of the C ABI.  Run with -m gpu on a B200."""
+import numpy as np
+import pytest
+
+import parity
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def frame1080(synth):
+    return synth.recipe_s(1920, 1080, seed=1234)
+
+
+def _scan_key(kps):
+    """Reference output order (src/sift.cpp:556-557,487-491): octave ascending is checkable from the record alone."""
+    return (kps["octave"] & 255).astype(np.int64)
+
+
+def test_1080p_properties(sift, frame1080):
+    kp, desc = sift.detect_describe(frame1080)
+    assert 2500 <= len(kp) <= 4500  # SURVEY: ~3.5 k keypoints on the seed-1234 frame
+    assert np.all(np.diff(_scan_key(kp)) >= 0)  # octaves appear in scan order
+    layer = (kp["octave"] >> 8) & 255
+    assert set(np.unique(layer)) <= {1, 2}  # nOctaveLayers = 2: extrema only on DoG layers 1..2
+    assert np.all((kp["angle"] >= 0) & (kp["angle"] < 360)) and np.all(kp["class_id"] == -1)
+    assert np.all(kp["response"] * 2 >= 0.04)  # contrast test, src/sift.cpp:365
+    assert np.allclose(np.linalg.norm(desc, axis=1), 1.0, atol=1e-5) and desc.min() >= 0 and desc.max() <= 1
+    # idempotence / determinism: the path has no order-dependent float atomics
+    kp2, desc2 = sift.detect_describe(frame1080)
+    assert kp.tobytes() == kp2.tobytes() and np.array_equal(desc, desc2)
+
+
+def test_1080p_vs_oracle(sift, oracle, frame1080):
+    """BASELINE config 2 at full size: the oracle needs ~1 s for this frame with all cores."""
+    okp, odesc, _, _, opq = oracle.f32().sift_ncl(frame1080, want_pyramids=True, want_prequant=True)
+    kp, desc = sift.detect_describe(frame1080)
+    pairs = parity.match_keypoints(kp, okp)
+    rec, prec = parity.recall_precision(pairs, len(kp), len(okp))
+    assert rec >= 0.99 and prec >= 0.99
+    pi = np.array([p[0] for p in pairs]); pj = np.array([p[1] for p in pairs])
+    frac, explained, unexplained, mx = parity.descriptor_report(desc[pi], odesc[pj], opq[pj])
+    assert frac >= 0.95 and unexplained <= len(pairs) // 200, (frac, explained, unexplained, mx)
+
+
+def test_batch_dev_equals_single_frames(pkg, synth):
+    """Config 4 in miniature: a device-resident batch (chunked internally) gives, per frame, exactly what the
+    one-image entry point gives; frames do not interact."""
+    import torch
+
+    frames = np.stack([synth.recipe_s(640, 360, seed=100 + k) for k in range(5)])
+    cap = 4096
+    s = pkg.Sift(360, 640, max_batch=2, max_kp_per_frame=cap)  # 5 frames in chunks of 2 -> ragged last chunk
+    d = torch.from_numpy(frames).cuda()
+    d_kp = torch.zeros((5, cap, 28), dtype=torch.uint8, device="cuda")
+    d_desc = torch.zeros((5, cap, 128), dtype=torch.float32, device="cuda")
+    d_cnt = torch.zeros(5, dtype=torch.int32, device="cuda")
+    s.detect_describe_batch_dev(d, d_kp, d_desc, d_cnt, cap, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    cnt = d_cnt.cpu().numpy()
+    for f in range(5):
+        kp, desc = s.detect_describe(frames[f])
+        assert cnt[f] == len(kp) > 50
+        got_kp = d_kp[f, : cnt[f]].cpu().numpy().view(pkg.KP_DTYPE).ravel()
+        assert got_kp.tobytes() == kp.tobytes()
+        assert np.array_equal(d_desc[f, : cnt[f]].cpu().numpy(), desc)
+    # host-buffer batch entry point: same answers again
+    h_kp = np.zeros((5, cap), dtype=pkg.KP_DTYPE); h_desc = np.zeros((5, cap, 128), dtype=np.float32); h_cnt = np.zeros(5, dtype=np.int32)
+    assert s.detect_describe_batch_host(frames, h_kp, h_desc, h_cnt, cap) == pkg.OK
+    assert np.array_equal(h_cnt, cnt)
+    for f in range(5):
+        assert np.array_equal(h_desc[f, : cnt[f]], d_desc[f, : cnt[f]].cpu().numpy())
+    # u8 front end (src/main.cpp:84-85: gray u8 -> float32 unscaled) == float path on the same integer-valued frames
+    u8 = np.clip(np.rint(frames), 0, 255).astype(np.uint8)
+    d8 = torch.from_numpy(u8).cuda()
+    d_cnt8 = torch.zeros(5, dtype=torch.int32, device="cuda")
+    d_desc8 = torch.zeros_like(d_desc)
+    s.detect_describe_batch_dev(d8, d_kp, d_desc8, d_cnt8, cap, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    kpf, descf = s.detect_describe(u8[0].astype(np.float32))
+    assert int(d_cnt8[0]) == len(kpf) and np.array_equal(d_desc8[0, : len(kpf)].cpu().numpy(), descf)
+    s.close()
+
+
+def test_edge_cases_and_errors(pkg, oracle, synth):
+    s = pkg.Sift(256, 256, max_batch=1, max_kp_per_frame=2048)
+    # smallest image the reference admits (16 px: octave 4 is 1x1) -> no keypoints, like the oracle
+    img = synth.recipe_s(16, 16, seed=1)
+    kp, desc = s.detect_describe(img)
+    assert len(kp) == len(oracle.f32().sift_ncl(img)[0]) == 0 and desc.shape == (0, 128)
+    # constant image: no extrema
+    assert len(s.detect_describe(np.full((64, 80), 128.0, np.float32))[0]) == 0
+    # below 16 px the reference throws inside cv::resize (src/sift.cpp:254) -> explicit status here
+    with pytest.raises(pkg.SiftError) as e:
+        s.detect_describe(np.zeros((12, 40), np.float32))
+    assert e.value.code == pkg.ERR_TOO_SMALL
+    with pytest.raises(pkg.SiftError) as e:
+        s.detect_describe(np.zeros((300, 300), np.float32))  # larger than the handle's workspace
+    assert e.value.code == pkg.ERR_ARG
+    # non-continuous input (row stride > cols*4) is honoured, unlike the reference which assumes continuous (:111)
+    big = synth.recipe_s(256, 200, seed=3, blobs_per_1080p=20000)
+    view = big[:, :180]
+    k1, d1 = s.detect_describe(view)
+    k2, d2 = s.detect_describe(np.ascontiguousarray(view))
+    assert len(k1) > 20 and k1.tobytes() == k2.tobytes() and np.array_equal(d1, d2)
+    # capacity overflow: status CAPACITY, true count reported, outputs = prefix of the full result
+    full_k, full_d = s.detect_describe(big)
+    cap = len(full_k) // 2
+    import ctypes as C
+    kps = np.zeros(cap, dtype=pkg.KP_DTYPE); desc = np.zeros((cap, 128), np.float32); n = C.c_int(0)
+    rc = pkg.lib().sift_b200_detect_describe(s._h, big.ctypes.data_as(C.c_void_p), big.shape[0], big.shape[1], C.c_size_t(0),
+                                             kps.ctypes.data_as(C.c_void_p), desc.ctypes.data_as(C.c_void_p), cap, C.byref(n))
+    assert rc == pkg.ERR_CAPACITY and n.value == len(full_k)
+    assert kps.tobytes() == full_k[:cap].tobytes() and np.array_equal(desc, full_d[:cap])
+    # calDescriptor's CV_Assert (src/sift.cpp:744): layer > nOctaveLayers+2 -> ASSERT status
+    g = s.build_gaussian_pyramid(big)
+    bad = full_k[:1].copy()
+    bad["octave"] = 0 | (7 << 8)
+    with pytest.raises(pkg.SiftError) as e:
+        s.cal_descriptor(g, big.shape[0], big.shape[1], bad)
+    assert e.value.code == pkg.ERR_ASSERT
+    assert s.cal_descriptor(g, big.shape[0], big.shape[1], full_k[:0]).shape == (0, 128)  # empty keypoint list
+    s.close()
+
+
+def test_launches_are_counted(pkg, synth):
+    s = pkg.Sift(128, 128, max_batch=1, max_kp_per_frame=1024)
+    n0 = s.launch_count()
+    s.detect_describe(synth.recipe_s(128, 128, seed=4))
+    assert s.launch_count() - n0 == 10  # base blur, 5 octaves, extrema, orientation, order+scan, descriptors
+    s.close()
