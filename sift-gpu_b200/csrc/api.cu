@@ -41,6 +41,14 @@ struct SiftB200 {
     float* d_desc = nullptr;
     int* d_counts = nullptr;
     int* h_counts = nullptr;    // pinned
+    // second staging set + copy streams for the pipelined host-batch entry point
+    float* d_img2 = nullptr;
+    SiftKeypoint* d_kp2 = nullptr;
+    float* d_desc2 = nullptr;
+    int* d_counts2 = nullptr;
+    int* h_counts2 = nullptr;
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    cudaEvent_t ev_in[2] = {}, ev_comp[2] = {}, ev_cnt[2] = {}, ev_out[2] = {};
     long long launches = 0;
     bool stage_timing = false;
     cudaEvent_t ev[8] = {};
@@ -230,6 +238,11 @@ int sift_b200_destroy(SiftB200* h) {
     cudaFree(h->db.order); cudaFree(h->db.kp_offset); cudaFree(h->db.sort_tmp);
     cudaFree(h->d_img); cudaFree(h->d_kp); cudaFree(h->d_desc); cudaFree(h->d_counts);
     cudaFreeHost(h->h_counts);
+    cudaFree(h->d_img2); cudaFree(h->d_kp2); cudaFree(h->d_desc2); cudaFree(h->d_counts2);
+    if (h->h_counts2) cudaFreeHost(h->h_counts2);
+    for (int b = 0; b < 2; ++b) for (cudaEvent_t e : {h->ev_in[b], h->ev_comp[b], h->ev_cnt[b], h->ev_out[b]}) if (e) cudaEventDestroy(e);
+    if (h->s_in) cudaStreamDestroy(h->s_in);
+    if (h->s_out) cudaStreamDestroy(h->s_out);
     for (auto& e : h->ev) if (e) cudaEventDestroy(e);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -257,6 +270,28 @@ static int ensure_staging(SiftB200* h) {
     return SIFT_B200_OK;
 }
 
+static int ensure_pipeline(SiftB200* h) {
+    if (h->d_img2) return SIFT_B200_OK;
+    const size_t F = h->max_batch;
+    CUDA_TRY(cudaMalloc((void**)&h->d_img2, F * (size_t)h->max_rows * h->max_cols * sizeof(float)));
+    CUDA_TRY(cudaMalloc((void**)&h->d_kp2, F * (size_t)h->cap_kp * sizeof(SiftKeypoint)));
+    CUDA_TRY(cudaMalloc((void**)&h->d_desc2, F * (size_t)h->cap_kp * 128 * sizeof(float)));
+    CUDA_TRY(cudaMalloc((void**)&h->d_counts2, F * sizeof(int)));
+    CUDA_TRY(cudaMallocHost((void**)&h->h_counts2, F * sizeof(int)));
+    CUDA_TRY(cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking));
+    for (int b = 0; b < 2; ++b) {
+        CUDA_TRY(cudaEventCreateWithFlags(&h->ev_in[b], cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&h->ev_comp[b], cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&h->ev_cnt[b], cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&h->ev_out[b], cudaEventDisableTiming));
+    }
+    return SIFT_B200_OK;
+}
+
+// Host batch, software-pipelined over chunks of max_batch frames: H2D of chunk k+1 (stream s_in) and the exact-size
+// D2H of chunk k-1 (stream s_out) overlap the kernels of chunk k (h->stream).  The host only ever waits for the tiny
+// counts copy of the PREVIOUS chunk, after the next chunk's work has been queued, so the GPU never idles on the host.
 int sift_b200_detect_describe_batch_host(SiftB200* h, const float* imgs, int n_frames, int rows, int cols, SiftKeypoint* kp_out, float* desc_out,
                                          int* counts_out, int cap) {
     int rc = check_dims(h, rows, cols);
@@ -264,27 +299,52 @@ int sift_b200_detect_describe_batch_host(SiftB200* h, const float* imgs, int n_f
     if (!imgs || !kp_out || !desc_out || !counts_out) return fail(SIFT_B200_ERR_ARG, "null buffer");
     CUDA_TRY(cudaSetDevice(h->device));
     if ((rc = ensure_staging(h))) return rc;
+    if ((rc = ensure_pipeline(h))) return rc;
     const size_t fs = (size_t)rows * cols;
+    float* d_img[2] = {h->d_img, h->d_img2};
+    SiftKeypoint* d_kp[2] = {h->d_kp, h->d_kp2};
+    float* d_desc[2] = {h->d_desc, h->d_desc2};
+    int* d_cnt[2] = {h->d_counts, h->d_counts2};
+    int* h_cnt[2] = {h->h_counts, h->h_counts2};
     int status = SIFT_B200_OK;
-    for (int f0 = 0; f0 < n_frames; f0 += h->max_batch) {
+    const int n_chunks = (n_frames + h->max_batch - 1) / h->max_batch;
+    auto flush = [&](int k) -> int {  // exact-size D2H of chunk k once its counts are on the host
+        const int b = k & 1, f0 = k * h->max_batch;
         const int nf = n_frames - f0 < h->max_batch ? n_frames - f0 : h->max_batch;
-        CUDA_TRY(cudaMemcpyAsync(h->d_img, imgs + f0 * fs, nf * fs * sizeof(float), cudaMemcpyHostToDevice, h->stream));
-        rc = run_pipeline(h, h->d_img, nullptr, nf, rows, cols, h->d_kp, h->d_desc, h->d_counts, cap, h->stream);
-        if (rc) return rc;
-        CUDA_TRY(cudaMemcpyAsync(h->h_counts, h->d_counts, nf * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-        CUDA_TRY(cudaStreamSynchronize(h->stream));
+        CUDA_TRY(cudaEventSynchronize(h->ev_cnt[b]));
         for (int f = 0; f < nf; ++f) {
-            int n = h->h_counts[f];
+            int n = h_cnt[b][f];
             counts_out[f0 + f] = n;
             if (n > cap) { n = cap; status = SIFT_B200_ERR_CAPACITY; }
             if (n > 0) {
-                CUDA_TRY(cudaMemcpyAsync(kp_out + (size_t)(f0 + f) * cap, h->d_kp + (size_t)f * cap, n * sizeof(SiftKeypoint), cudaMemcpyDeviceToHost, h->stream));
-                CUDA_TRY(cudaMemcpyAsync(desc_out + (size_t)(f0 + f) * cap * 128, h->d_desc + (size_t)f * cap * 128, (size_t)n * 128 * sizeof(float),
-                                         cudaMemcpyDeviceToHost, h->stream));
+                CUDA_TRY(cudaMemcpyAsync(kp_out + (size_t)(f0 + f) * cap, d_kp[b] + (size_t)f * cap, n * sizeof(SiftKeypoint), cudaMemcpyDeviceToHost, h->s_out));
+                CUDA_TRY(cudaMemcpyAsync(desc_out + (size_t)(f0 + f) * cap * 128, d_desc[b] + (size_t)f * cap * 128, (size_t)n * 128 * sizeof(float),
+                                         cudaMemcpyDeviceToHost, h->s_out));
             }
         }
-        CUDA_TRY(cudaStreamSynchronize(h->stream));
+        CUDA_TRY(cudaEventRecord(h->ev_out[b], h->s_out));
+        return SIFT_B200_OK;
+    };
+    for (int k = 0; k < n_chunks; ++k) {
+        const int b = k & 1, f0 = k * h->max_batch;
+        const int nf = n_frames - f0 < h->max_batch ? n_frames - f0 : h->max_batch;
+        if (k >= 2) CUDA_TRY(cudaStreamWaitEvent(h->s_in, h->ev_comp[b], 0));   // chunk k-2 has consumed this input buffer
+        CUDA_TRY(cudaMemcpyAsync(d_img[b], imgs + f0 * fs, nf * fs * sizeof(float), cudaMemcpyHostToDevice, h->s_in));
+        CUDA_TRY(cudaEventRecord(h->ev_in[b], h->s_in));
+        CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_in[b], 0));
+        if (k >= 2) CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_out[b], 0)); // chunk k-2's results have left this output buffer
+        rc = run_pipeline(h, d_img[b], nullptr, nf, rows, cols, d_kp[b], d_desc[b], d_cnt[b], cap, h->stream);
+        if (rc) return rc;
+        CUDA_TRY(cudaEventRecord(h->ev_comp[b], h->stream));
+        // results of chunk k-1 go out on s_out WHILE chunk k computes (queued before the wait on chunk k below)
+        if (k >= 1 && (rc = flush(k - 1))) return rc;
+        CUDA_TRY(cudaStreamWaitEvent(h->s_out, h->ev_comp[b], 0));
+        CUDA_TRY(cudaMemcpyAsync(h_cnt[b], d_cnt[b], nf * sizeof(int), cudaMemcpyDeviceToHost, h->s_out));
+        CUDA_TRY(cudaEventRecord(h->ev_cnt[b], h->s_out));
     }
+    if (n_chunks > 0 && (rc = flush(n_chunks - 1))) return rc;
+    CUDA_TRY(cudaStreamSynchronize(h->s_out));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
     if (status) g_err = "keypoint capacity exceeded: outputs truncated";
     return status;
 }

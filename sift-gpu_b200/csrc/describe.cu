@@ -27,8 +27,9 @@ constexpr int DT = 128;        // threads per CTA = output elements
 constexpr int MAXR = 40;       // radius = cvRound(3*scl*sqrt2*2.5), scl_octv < 3.81  
 constexpr int MAXW = 2 * MAXR + 1;
 constexpr int SLOTS = DT / 16; // row slots per cell
-constexpr int DESC_SMEM_FLOATS = 2 * MAXW * MAXW + (DB + 1) * DT + 8;
-constexpr int DESC_SMEM_BYTES = DESC_SMEM_FLOATS * 4;
+constexpr int SMALL_R = 28;     // radius class boundary (most layer-1 keypoints)
+__host__ __device__ constexpr int desc_smem_bytes(int r) { return (2 * (2 * r + 1) * (2 * r + 1) + (DB + 1) * DT + 8) * 4; }
+constexpr int DESC_SMEM_BYTES = desc_smem_bytes(MAXR);
 
 __device__ __forceinline__ int cv_round(float v) { return __float2int_rn(v); }
 __device__ __forceinline__ int cv_floor(float v) { return __float2int_rd(v); }
@@ -62,9 +63,31 @@ __device__ __forceinline__ float block_sum(float v, float* red, int tid) {
     return (red[0] + red[1]) + (red[2] + red[3]);
 }
 
+// window radius of calcSIFTDescriptor (:587-590)
+__device__ __forceinline__ int descr_radius(float scl, int rows, int cols) {
+    const float hist_width = 3.f * scl;
+    const int radius = cv_round(hist_width * 1.4142135623730951f * (DW + 1) * 0.5f);
+    const int diag = (int)sqrt(((double)cols) * cols + ((double)rows) * rows);
+    return min(radius, diag);
+}
+
+// conservative j-interval of {lo_v < j*k + off < hi_v}, intersected into [lo, hi]; false when the row misses the slab
+__device__ __forceinline__ bool slab(float k, float inv_k, float off, float lo_v, float hi_v, float& lo, float& hi) {
+    if (inv_k != 0.f) {
+        const float u0 = (lo_v - off) * inv_k, u1 = (hi_v - off) * inv_k;
+        lo = fmaxf(lo, fminf(u0, u1));
+        hi = fminf(hi, fmaxf(u0, u1));
+        return true;
+    }
+    return off > lo_v - 0.01f && off < hi_v + 0.01f;  // k ~ 0: the row is inside or outside as a whole
+}
+
+struct Sample { float mw, ob; };
+
 // calcSIFTDescriptor, src/sift.cpp:579-722, for one keypoint by one CTA.  dst: 128 floats in global memory.
-__device__ void calc_descriptor(const float* __restrict__ img, int rows, int cols, int pitch, float ptx, float pty, float ori, float scl,
-                                float* __restrict__ smem, float* __restrict__ dst) {
+// wmax: row pitch of the staging arrays (>= 2*radius+1).
+__device__ void calc_descriptor(const float* __restrict__ img, int rows, int cols, int pitch, float ptx, float pty, float ori, float scl, int radius,
+                                int wmax, float* __restrict__ smem, float* __restrict__ dst) {
     const int tid = threadIdx.x;
     const int px = cv_round(ptx), py = cv_round(pty);
     float cos_t = cosf(ori * (float)(3.1415926535897932384626433832795 / 180));
@@ -72,43 +95,75 @@ __device__ void calc_descriptor(const float* __restrict__ img, int rows, int col
     const float bins_per_rad = DB / 360.f;
     const float exp_scale = -1.f / (DW * DW * 0.5f);
     const float hist_width = 3.f * scl;
-    int radius = cv_round(hist_width * 1.4142135623730951f * (DW + 1) * 0.5f);
-    const int diag = (int)sqrt(((double)cols) * cols + ((double)rows) * rows);
-    radius = min(radius, diag);
-    radius = min(radius, MAXR);  // never binds for keypoints produced by this pipeline (scl_octv < 3.81)
     cos_t /= hist_width;
     sin_t /= hist_width;
-    const int w = 2 * radius + 1;
+    const int w = wmax;
     float* s_mag = smem;
-    float* s_ob = smem + MAXW * MAXW;
-    float* s_priv = smem + 2 * MAXW * MAXW;  // [DB+1][DT]
+    float* s_ob = smem + wmax * wmax;
+    float* s_priv = smem + 2 * wmax * wmax;  // [DB+1][DT]
     float* s_red = s_priv + (DB + 1) * DT;
+    const float inv_s = fabsf(sin_t) > 1e-6f ? 1.f / sin_t : 0.f;
+    const float inv_c = fabsf(cos_t) > 1e-6f ? 1.f / cos_t : 0.f;
+    const int jmin = max(-radius, 1 - px), jmax = min(radius, cols - 2 - px);   // 0 < c < cols-1
+    const int imin = max(-radius, 1 - py), imax = min(radius, rows - 2 - py);   // 0 < r < rows-1
 
-    // ---- phase 1: evaluate every window sample once (warp = window row, lanes = consecutive columns) ----
-    for (int i = -radius + (tid >> 5); i <= radius; i += DT / 32) {
-        const int r = py + i;
-        const bool row_ok = r > 0 && r < rows - 1;
-        const float* rowp = img + (size_t)r * pitch;
-        for (int j = -radius + (tid & 31); j <= radius; j += 32) {
-            const float c_rot = j * cos_t - i * sin_t;
-            const float r_rot = j * sin_t + i * cos_t;
-            const float rbin = r_rot + DW / 2 - 0.5f;
-            const float cbin = c_rot + DW / 2 - 0.5f;
-            const int c = px + j;
-            float mw = 0.f, ob = 0.f;
-            if (row_ok && rbin > -1 && rbin < DW && cbin > -1 && cbin < DW && c > 0 && c < cols - 1) {
-                const float* q = rowp + c;
-                const float dx = __ldg(q + 1) - __ldg(q - 1);
-                const float dy = __ldg(q - pitch) - __ldg(q + pitch);
-                const float o_ = fast_atan2_deg(dy, dx);
-                const float m_ = sqrtf(dx * dx + dy * dy);
-                const float w_ = expf((c_rot * c_rot + r_rot * r_rot) * exp_scale);
-                ob = (o_ - ori) * bins_per_rad;
-                mw = m_ * w_;
+    // ---- phase 1: evaluate every ACCEPTED window sample once.  warp = window row (two rows in flight), lanes =
+    // consecutive columns of the row's accepted interval: -1 < rbin < 4 and -1 < cbin < 4 (:620), i.e. the two slab
+    // inequalities in j, widened by one pixel; the exact reference test decides.  Positions outside the interval are
+    // never read by phase 2 (its supports lie inside the accepted region).
+    {
+        const int lane = tid & 31, wrp = tid >> 5;
+        for (int i0 = imin + wrp; i0 <= imax; i0 += 2 * (DT / 32)) {
+            int jlo[2], jhi[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int i = i0 + u * (DT / 32);
+                float lo = (float)jmin, hi = (float)jmax;
+                bool ok = i <= imax;
+                ok = ok && slab(sin_t, inv_s, i * cos_t + 1.5f, -1.f, 4.f, lo, hi);
+                ok = ok && slab(cos_t, inv_c, -(i * sin_t) + 1.5f, -1.f, 4.f, lo, hi);
+                jlo[u] = ok ? max(jmin, (int)floorf(lo) - 1) : 1;
+                jhi[u] = ok ? min(jmax, (int)ceilf(hi) + 1) : 0;
             }
-            const int idx = (i + radius) * w + (j + radius);
-            s_mag[idx] = mw;
-            s_ob[idx] = ob;
+            const int steps = max(jhi[0] - jlo[0], jhi[1] - jlo[1]) / 32 + 1;
+            for (int t = 0; t < steps; ++t) {
+                float dxv[2], dyv[2], crot[2], rrot[2];
+                bool acc[2];
+                int idx[2];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {  // tests and loads of both rows first: 8 independent loads in flight
+                    const int i = i0 + u * (DT / 32), j = jlo[u] + lane + 32 * t;
+                    const float c_rot = j * cos_t - i * sin_t;
+                    const float r_rot = j * sin_t + i * cos_t;
+                    const float rbin = r_rot + DW / 2 - 0.5f;
+                    const float cbin = c_rot + DW / 2 - 0.5f;
+                    acc[u] = j <= jhi[u] && rbin > -1 && rbin < DW && cbin > -1 && cbin < DW;
+                    idx[u] = (i + radius) * w + (j + radius);
+                    crot[u] = c_rot; rrot[u] = r_rot;
+                    dxv[u] = dyv[u] = 0.f;
+                    if (acc[u]) {
+                        const float* q = img + (size_t)(py + i) * pitch + (px + j);
+                        dxv[u] = __ldg(q + 1) - __ldg(q - 1);
+                        dyv[u] = __ldg(q - pitch) - __ldg(q + pitch);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int j = jlo[u] + lane + 32 * t;
+                    if (j <= jhi[u]) {
+                        float mw = 0.f, ob = 0.f;
+                        if (acc[u]) {
+                            const float o_ = fast_atan2_deg(dyv[u], dxv[u]);
+                            const float m_ = sqrtf(dxv[u] * dxv[u] + dyv[u] * dyv[u]);
+                            const float w_ = expf((crot[u] * crot[u] + rrot[u] * rrot[u]) * exp_scale);
+                            ob = (o_ - ori) * bins_per_rad;
+                            mw = m_ * w_;
+                        }
+                        s_mag[idx[u]] = mw;
+                        s_ob[idx[u]] = ob;
+                    }
+                }
+            }
         }
     }
 #pragma unroll
@@ -124,28 +179,16 @@ __device__ void calc_descriptor(const float* __restrict__ img, int rows, int col
         const float rr = (a - 1.5f) * hist_width, cr = (b - 1.5f) * hist_width;
         const float ic = -cr * st + rr * ct;
         const float ext = hist_width * (fabsf(ct) + fabsf(st)) + 1.5f;
-        int ilo = max(-radius, (int)ceilf(ic - ext));
-        int ihi = min(radius, (int)floorf(ic + ext));
-        ilo = max(ilo, 1 - py);
-        ihi = min(ihi, rows - 2 - py);
-        const float inv_s = fabsf(sin_t) > 1e-6f ? 1.f / sin_t : 0.f;
-        const float inv_c = fabsf(cos_t) > 1e-6f ? 1.f / cos_t : 0.f;
+        const int ilo = max(imin, (int)ceilf(ic - ext));
+        const int ihi = min(imax, (int)floorf(ic + ext));
         float* priv = s_priv + tid;
         for (int i = ilo + slot; i <= ihi; i += SLOTS) {
             // a-1 <= rbin < a+1 with rbin = j*sin_t + i*cos_t + 1.5 ;  b-1 <= cbin < b+1 with cbin = j*cos_t - i*sin_t + 1.5
-            float lo = (float)-radius, hi = (float)radius;
-            if (inv_s != 0.f) {
-                const float u0 = (a - 2.5f - i * cos_t) * inv_s, u1 = (a - 0.5f - i * cos_t) * inv_s;
-                lo = fmaxf(lo, fminf(u0, u1));
-                hi = fminf(hi, fmaxf(u0, u1));
-            }
-            if (inv_c != 0.f) {
-                const float u0 = (b - 2.5f + i * sin_t) * inv_c, u1 = (b - 0.5f + i * sin_t) * inv_c;
-                lo = fmaxf(lo, fminf(u0, u1));
-                hi = fminf(hi, fmaxf(u0, u1));
-            }
-            int jlo = max(max(-radius, 1 - px), (int)floorf(lo) - 1);
-            int jhi = min(min(radius, cols - 2 - px), (int)ceilf(hi) + 1);
+            float lo = (float)jmin, hi = (float)jmax;
+            if (!slab(sin_t, inv_s, i * cos_t + 1.5f, a - 1.f, a + 1.f, lo, hi)) continue;
+            if (!slab(cos_t, inv_c, -(i * sin_t) + 1.5f, b - 1.f, b + 1.f, lo, hi)) continue;
+            const int jlo = max(jmin, (int)floorf(lo) - 1);
+            const int jhi = min(jmax, (int)ceilf(hi) + 1);
             const int base = (i + radius) * w + radius;
             for (int j = jlo; j <= jhi; ++j) {
                 const float c_rot = j * cos_t - i * sin_t;
@@ -154,8 +197,9 @@ __device__ void calc_descriptor(const float* __restrict__ img, int rows, int col
                 float cbin = c_rot + DW / 2 - 0.5f;
                 const int r0 = cv_floor(rbin), c0 = cv_floor(cbin);
                 if ((unsigned)(a - r0) > 1u || (unsigned)(b - c0) > 1u) continue;
+                if (!(rbin > -1 && cbin > -1)) continue;  // rbin == -1 exactly is rejected by the reference (:620)
                 const float mag = s_mag[base + j];
-                if (mag == 0.f) continue;  // rejected sample (or zero vote): contributes +0
+                if (mag == 0.f) continue;  // zero vote: contributes +0
                 float obin = s_ob[base + j];
                 rbin -= r0;
                 cbin -= c0;
@@ -202,8 +246,9 @@ __device__ void calc_descriptor(const float* __restrict__ img, int rows, int col
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(DT)
-    describe_kernel(const __grid_constant__ PyrView pv, const DetectBuf db, SiftKeypoint* __restrict__ kp_out, float* __restrict__ desc_out, int cap) {
+__global__ void __launch_bounds__(DT, 7)
+    describe_kernel(const __grid_constant__ PyrView pv, const DetectBuf db, SiftKeypoint* __restrict__ kp_out, float* __restrict__ desc_out, int cap,
+                    int r_lo, int r_hi) {  // this launch handles keypoints with r_lo < window radius <= r_hi (staging sized for r_hi)
     extern __shared__ float smem[];
     const int f = blockIdx.y;
     int n = db.n_refined[f];
@@ -219,13 +264,16 @@ __global__ void __launch_bounds__(DT)
         const OctaveView& ov = pv.oct[octave];
         const float* img = ov.G[layer] + (size_t)f * ov.frame_stride;
         const float size = rec.size * scale;
+        const int radius = descr_radius(size * 0.5f, ov.rows, ov.cols);
+        if (radius <= r_lo || radius > r_hi) continue;
         for (int k = 0; k < np; ++k) {
             const int slot = base + k;
             if (slot >= cap) break;
             const float kp_angle = db.angles[((size_t)f * db.cap_r + i) * kMaxPeaks + k];
             float angle = 360.f - kp_angle;
             if (fabsf(angle - 360.f) < 1.1920928955078125e-7f) angle = 0.f;
-            calc_descriptor(img, ov.rows, ov.cols, ov.pitch, rec.x * scale, rec.y * scale, angle, size * 0.5f, smem, desc_out + ((size_t)f * cap + slot) * 128);
+            calc_descriptor(img, ov.rows, ov.cols, ov.pitch, rec.x * scale, rec.y * scale, angle, size * 0.5f, radius, 2 * r_hi + 1, smem,
+                            desc_out + ((size_t)f * cap + slot) * 128);
             if (threadIdx.x == 0) {
                 SiftKeypoint kp;
                 kp.x = rec.x; kp.y = rec.y; kp.size = rec.size; kp.angle = kp_angle; kp.response = rec.response;
@@ -255,13 +303,12 @@ __global__ void __launch_bounds__(DT)
         float angle = 360.f - kp.angle;
         if (fabsf(angle - 360.f) < 1.1920928955078125e-7f) angle = 0.f;
         const float size = kp.size * scale;
-        const float hw = 3.f * (size * 0.5f);
-        const int diag = (int)sqrt(((double)ov.cols) * ov.cols + ((double)ov.rows) * ov.rows);
-        if (min(cv_round(hw * 1.4142135623730951f * (DW + 1) * 0.5f), diag) > MAXR) {
+        const int radius = descr_radius(size * 0.5f, ov.rows, ov.cols);
+        if (radius > MAXR) {
             if (threadIdx.x == 0) atomicExch(err, 2);  // window larger than this kernel's staging (scl_octv > 3.8)
             continue;
         }
-        calc_descriptor(ov.G[layer], ov.rows, ov.cols, ov.pitch, kp.x * scale, kp.y * scale, angle, size * 0.5f, smem, desc_out + (size_t)p * 128);
+        calc_descriptor(ov.G[layer], ov.rows, ov.cols, ov.pitch, kp.x * scale, kp.y * scale, angle, size * 0.5f, radius, MAXW, smem, desc_out + (size_t)p * 128);
     }
 }
 
@@ -273,9 +320,11 @@ void init_describe_kernels() {
 }
 
 int launch_describe(const PyrView& pv, const DetectBuf& db, int n_frames, SiftKeypoint* d_kp, float* d_desc, int cap, cudaStream_t st) {
+    // two radius classes so that the common small windows (layer 1: radius <= 28) run at ~2x the occupancy
     dim3 grid(148 * 4, n_frames);
-    describe_kernel<<<grid, DT, DESC_SMEM_BYTES, st>>>(pv, db, d_kp, d_desc, cap);
-    return 1;
+    describe_kernel<<<grid, DT, desc_smem_bytes(SMALL_R), st>>>(pv, db, d_kp, d_desc, cap, -1, SMALL_R);
+    describe_kernel<<<grid, DT, desc_smem_bytes(MAXR), st>>>(pv, db, d_kp, d_desc, cap, SMALL_R, MAXR);
+    return 2;
 }
 
 int launch_describe_given(const PyrView& pv, const SiftKeypoint* d_kps, int n, float* d_desc, int first_octave, int* d_err, cudaStream_t st) {
