@@ -205,6 +205,9 @@ int sift_b200_create(SiftB200** out, int max_rows, int max_cols, int max_batch, 
     db.cap_r = max_kp_per_frame;
     db.cap_r_pow2 = next_pow2(db.cap_r);
     const size_t F = max_batch, C = db.cap_r;
+    db.cap_c = 4 * db.cap_r < 16384 ? 16384 : 4 * db.cap_r;  // extrema before refinement (20-85 % survive)
+    CUDA_TRY(cudaMalloc((void**)&db.cand, F * (size_t)db.cap_c * sizeof(uint32_t)));
+    CUDA_TRY(cudaMalloc((void**)&db.n_cand, F * sizeof(int)));
     CUDA_TRY(cudaMalloc((void**)&db.refined, F * C * sizeof(Refined)));
     CUDA_TRY(cudaMalloc((void**)&db.n_refined, F * sizeof(int)));
     CUDA_TRY(cudaMalloc((void**)&db.angles, F * C * kMaxPeaks * sizeof(float)));
@@ -234,6 +237,7 @@ int sift_b200_destroy(SiftB200* h) {
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
     cudaFree(h->ws); cudaFree(h->ws_full);
+    cudaFree(h->db.cand); cudaFree(h->db.n_cand);
     cudaFree(h->db.refined); cudaFree(h->db.n_refined); cudaFree(h->db.angles); cudaFree(h->db.n_peaks);
     cudaFree(h->db.order); cudaFree(h->db.kp_offset); cudaFree(h->db.sort_tmp);
     cudaFree(h->d_img); cudaFree(h->d_kp); cudaFree(h->d_desc); cudaFree(h->d_counts);

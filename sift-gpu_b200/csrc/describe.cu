@@ -34,22 +34,19 @@ constexpr int DESC_SMEM_BYTES = desc_smem_bytes(MAXR);
 __device__ __forceinline__ int cv_round(float v) { return __float2int_rn(v); }
 __device__ __forceinline__ int cv_floor(float v) { return __float2int_rd(v); }
 
+// hal::fastAtan2 (degrees).  Branch-free min/max form of the scalar polynomial in oracle/oracle_prims.h: the quotient is
+// min/(max + eps) in both octants, so one division serves both and the result is bit-identical.
 __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
     const float s = (float)(180.0 / 3.1415926535897932384626433832795);
     const float p1 = 0.9997878412794807f * s, p3 = -0.3258083974640975f * s, p5 = 0.1555786518463281f * s, p7 = -0.04432655554792128f * s;
     const float ax = fabsf(x), ay = fabsf(y);
-    float a, c, c2;
-    if (ax >= ay) {
-        c = ay / (ax + (float)2.2204460492503131e-16);
-        c2 = c * c;
-        a = (((p7 * c2 + p5) * c2 + p3) * c2 + p1) * c;
-    } else {
-        c = ax / (ay + (float)2.2204460492503131e-16);
-        c2 = c * c;
-        a = 90.f - (((p7 * c2 + p5) * c2 + p3) * c2 + p1) * c;
-    }
-    if (x < 0) a = 180.f - a;
-    if (y < 0) a = 360.f - a;
+    const float mn = fminf(ax, ay), mx = fmaxf(ax, ay);
+    const float c = mn / (mx + (float)2.2204460492503131e-16);
+    const float c2 = c * c;
+    float a = (((p7 * c2 + p5) * c2 + p3) * c2 + p1) * c;
+    a = ax >= ay ? a : 90.f - a;
+    a = x < 0 ? 180.f - a : a;
+    a = y < 0 ? 360.f - a : a;
     return a;
 }
 
@@ -107,61 +104,46 @@ __device__ void calc_descriptor(const float* __restrict__ img, int rows, int col
     const int jmin = max(-radius, 1 - px), jmax = min(radius, cols - 2 - px);   // 0 < c < cols-1
     const int imin = max(-radius, 1 - py), imax = min(radius, rows - 2 - py);   // 0 < r < rows-1
 
-    // ---- phase 1: evaluate every ACCEPTED window sample once.  warp = window row (two rows in flight), lanes =
-    // consecutive columns of the row's accepted interval: -1 < rbin < 4 and -1 < cbin < 4 (:620), i.e. the two slab
-    // inequalities in j, widened by one pixel; the exact reference test decides.  Positions outside the interval are
-    // never read by phase 2 (its supports lie inside the accepted region).
+    // ---- phase 1: evaluate every ACCEPTED window sample once.  An 8-lane group owns a window row (16 rows in flight per
+    // CTA); its lanes walk the row's accepted interval -1 < rbin < 4, -1 < cbin < 4 (:620) -- the two slab inequalities in j,
+    // widened by one pixel; the exact reference test decides -- two samples per lane per step so that 8 independent
+    // gradient loads are in flight.  The body is branch-free (rejected samples compute on real pixels and store 0).
+    // Positions outside the interval are never read by phase 2 (its supports lie inside the accepted region).
     {
-        const int lane = tid & 31, wrp = tid >> 5;
-        for (int i0 = imin + wrp; i0 <= imax; i0 += 2 * (DT / 32)) {
-            int jlo[2], jhi[2];
+        const int gl = tid & 7, grp = tid >> 3;
+        for (int i = imin + grp; i <= imax; i += DT / 8) {
+            float lo = (float)jmin, hi = (float)jmax;
+            if (!slab(sin_t, inv_s, i * cos_t + 1.5f, -1.f, 4.f, lo, hi)) continue;
+            if (!slab(cos_t, inv_c, -(i * sin_t) + 1.5f, -1.f, 4.f, lo, hi)) continue;
+            const int jlo = max(jmin, (int)floorf(lo) - 1);
+            const int jhi = min(jmax, (int)ceilf(hi) + 1);
+            const float* rowp = img + (size_t)(py + i) * pitch + px;
+            float* mrow = s_mag + (i + radius) * w + radius;
+            float* orow = s_ob + (i + radius) * w + radius;
+            const float isin = i * sin_t, icos = i * cos_t;
+            for (int j0 = jlo + gl; j0 <= jhi; j0 += 16) {
+                float dxv[2], dyv[2];
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                const int i = i0 + u * (DT / 32);
-                float lo = (float)jmin, hi = (float)jmax;
-                bool ok = i <= imax;
-                ok = ok && slab(sin_t, inv_s, i * cos_t + 1.5f, -1.f, 4.f, lo, hi);
-                ok = ok && slab(cos_t, inv_c, -(i * sin_t) + 1.5f, -1.f, 4.f, lo, hi);
-                jlo[u] = ok ? max(jmin, (int)floorf(lo) - 1) : 1;
-                jhi[u] = ok ? min(jmax, (int)ceilf(hi) + 1) : 0;
-            }
-            const int steps = max(jhi[0] - jlo[0], jhi[1] - jlo[1]) / 32 + 1;
-            for (int t = 0; t < steps; ++t) {
-                float dxv[2], dyv[2], crot[2], rrot[2];
-                bool acc[2];
-                int idx[2];
-#pragma unroll
-                for (int u = 0; u < 2; ++u) {  // tests and loads of both rows first: 8 independent loads in flight
-                    const int i = i0 + u * (DT / 32), j = jlo[u] + lane + 32 * t;
-                    const float c_rot = j * cos_t - i * sin_t;
-                    const float r_rot = j * sin_t + i * cos_t;
-                    const float rbin = r_rot + DW / 2 - 0.5f;
-                    const float cbin = c_rot + DW / 2 - 0.5f;
-                    acc[u] = j <= jhi[u] && rbin > -1 && rbin < DW && cbin > -1 && cbin < DW;
-                    idx[u] = (i + radius) * w + (j + radius);
-                    crot[u] = c_rot; rrot[u] = r_rot;
-                    dxv[u] = dyv[u] = 0.f;
-                    if (acc[u]) {
-                        const float* q = img + (size_t)(py + i) * pitch + (px + j);
-                        dxv[u] = __ldg(q + 1) - __ldg(q - 1);
-                        dyv[u] = __ldg(q - pitch) - __ldg(q + pitch);
-                    }
+                for (int u = 0; u < 2; ++u) {
+                    const int j = min(j0 + 8 * u, jmax);  // clamped: always an interior pixel, loads are unconditional
+                    const float* q = rowp + j;
+                    dxv[u] = __ldg(q + 1) - __ldg(q - 1);
+                    dyv[u] = __ldg(q - pitch) - __ldg(q + pitch);
                 }
 #pragma unroll
                 for (int u = 0; u < 2; ++u) {
-                    const int j = jlo[u] + lane + 32 * t;
-                    if (j <= jhi[u]) {
-                        float mw = 0.f, ob = 0.f;
-                        if (acc[u]) {
-                            const float o_ = fast_atan2_deg(dyv[u], dxv[u]);
-                            const float m_ = sqrtf(dxv[u] * dxv[u] + dyv[u] * dyv[u]);
-                            const float w_ = expf((crot[u] * crot[u] + rrot[u] * rrot[u]) * exp_scale);
-                            ob = (o_ - ori) * bins_per_rad;
-                            mw = m_ * w_;
-                        }
-                        s_mag[idx[u]] = mw;
-                        s_ob[idx[u]] = ob;
-                    }
+                    const int j = j0 + 8 * u;
+                    const float c_rot = j * cos_t - isin;
+                    const float r_rot = j * sin_t + icos;
+                    const float rbin = r_rot + DW / 2 - 0.5f;
+                    const float cbin = c_rot + DW / 2 - 0.5f;
+                    const bool acc = rbin > -1 && rbin < DW && cbin > -1 && cbin < DW;
+                    const float o_ = fast_atan2_deg(dyv[u], dxv[u]);
+                    const float m_ = sqrtf(dxv[u] * dxv[u] + dyv[u] * dyv[u]);
+                    const float w_ = expf((c_rot * c_rot + r_rot * r_rot) * exp_scale);
+                    const float ob = (o_ - ori) * bins_per_rad;
+                    const float mw = acc ? m_ * w_ : 0.f;
+                    if (j <= jhi) { mrow[j] = mw; orow[j] = ob; }
                 }
             }
         }

@@ -23,23 +23,18 @@ namespace {
 
 __device__ __forceinline__ int cv_round(float v) { return __float2int_rn(v); }  // cvRound: round half to even
 
-// hal::fastAtan2 scalar polynomial (degrees); same operations as oracle/oracle_prims.h.
+// hal::fastAtan2 (degrees): branch-free min/max form of the scalar polynomial in oracle/oracle_prims.h (bit-identical).
 __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
     const float s = (float)(180.0 / 3.1415926535897932384626433832795);
     const float p1 = 0.9997878412794807f * s, p3 = -0.3258083974640975f * s, p5 = 0.1555786518463281f * s, p7 = -0.04432655554792128f * s;
     const float ax = fabsf(x), ay = fabsf(y);
-    float a, c, c2;
-    if (ax >= ay) {
-        c = ay / (ax + (float)2.2204460492503131e-16);
-        c2 = c * c;
-        a = (((p7 * c2 + p5) * c2 + p3) * c2 + p1) * c;
-    } else {
-        c = ax / (ay + (float)2.2204460492503131e-16);
-        c2 = c * c;
-        a = 90.f - (((p7 * c2 + p5) * c2 + p3) * c2 + p1) * c;
-    }
-    if (x < 0) a = 180.f - a;
-    if (y < 0) a = 360.f - a;
+    const float mn = fminf(ax, ay), mx = fmaxf(ax, ay);
+    const float c = mn / (mx + (float)2.2204460492503131e-16);
+    const float c2 = c * c;
+    float a = (((p7 * c2 + p5) * c2 + p3) * c2 + p1) * c;
+    a = ax >= ay ? a : 90.f - a;
+    a = x < 0 ? 180.f - a : a;
+    a = y < 0 ? 360.f - a : a;
     return a;
 }
 
@@ -139,28 +134,33 @@ __global__ void __launch_bounds__(EX_WARPS * 32) extrema_kernel(const __grid_con
     const int r_begin = kImgBorder + (t / ov.tiles_x) * EX_ROWS;
     const int r_end = min(r_begin + EX_ROWS, rows - kImgBorder);  // exclusive
     const size_t foff = (size_t)f * ov.frame_stride;
-    const float* D[4] = {ov.D[0] + foff, ov.D[1] + foff, ov.D[2] + foff, ov.D[3] + foff};
     const bool col_in = c < cols;
     const bool col_out = lane >= 1 && lane <= EX_COLS && c < cols - kImgBorder;
+    const float* p0 = ov.D[0] + foff + (size_t)(r_begin - 1) * pitch + (col_in ? c : 0);
+    const float* p1 = ov.D[1] + foff + (size_t)(r_begin - 1) * pitch + (col_in ? c : 0);
+    const float* p2 = ov.D[2] + foff + (size_t)(r_begin - 1) * pitch + (col_in ? c : 0);
+    const float* p3 = ov.D[3] + foff + (size_t)(r_begin - 1) * pitch + (col_in ? c : 0);
 
     float hmaxA[4], hminA[4], hmaxB[4], hminB[4], cenB[2];
 #pragma unroll
     for (int l = 0; l < 4; ++l) { hmaxA[l] = hmaxB[l] = -3.4e38f; hminA[l] = hminB[l] = 3.4e38f; }
     cenB[0] = cenB[1] = 0.f;
+    float nx[4] = {__ldg(p0), __ldg(p1), __ldg(p2), __ldg(p3)};  // row r_begin-1
 #pragma unroll 1
     for (int y = r_begin - 1; y <= r_end; ++y) {
-        float hmaxC[4], hminC[4], cenC[2];
+        float v[4] = {nx[0], nx[1], nx[2], nx[3]};
+        if (y < r_end) {  // prefetch row y+1 (<= rows-5) while row y is processed
+            p0 += pitch; p1 += pitch; p2 += pitch; p3 += pitch;
+            nx[0] = __ldg(p0); nx[1] = __ldg(p1); nx[2] = __ldg(p2); nx[3] = __ldg(p3);
+        }
+        float hmaxC[4], hminC[4];
 #pragma unroll
         for (int l = 0; l < 4; ++l) {
-            const float v = col_in ? __ldg(D[l] + (size_t)y * pitch + c) : 0.f;
-            const float vl = __shfl_up_sync(0xffffffffu, v, 1), vr = __shfl_down_sync(0xffffffffu, v, 1);
-            hmaxC[l] = fmaxf(v, fmaxf(vl, vr));
-            hminC[l] = fminf(v, fminf(vl, vr));
-            if (l == 1) cenC[0] = v;
-            if (l == 2) cenC[1] = v;
+            const float vl = __shfl_up_sync(0xffffffffu, v[l], 1), vr = __shfl_down_sync(0xffffffffu, v[l], 1);
+            hmaxC[l] = fmaxf(v[l], fmaxf(vl, vr));
+            hminC[l] = fminf(v[l], fminf(vl, vr));
         }
         if (y >= r_begin + 1) {  // rows y-2, y-1, y are in flight: test row y-1
-            const int r = y - 1;
             float M[4], m[4];
 #pragma unroll
             for (int l = 0; l < 4; ++l) {
@@ -174,19 +174,35 @@ __global__ void __launch_bounds__(EX_WARPS * 32) extrema_kernel(const __grid_con
                 const bool hit = col_out && ((val > 8.0f && val >= fmaxf(M[layer0 - 1], fmaxf(M[layer0], M[layer0 + 1]))) ||
                                              (val < -8.0f && val <= fminf(m[layer0 - 1], fminf(m[layer0], m[layer0 + 1]))));
                 if (hit) {
-                    int r1 = r, c1 = c, layer = layer0;
-                    Refined rec;
-                    if (adjust_local_extrema(D, rows, cols, pitch, o, layer, r1, c1, rec)) {
-                        rec.key = ((uint32_t)o << 27) | ((uint32_t)(layer0 - 1) << 26) | ((uint32_t)r << 13) | (uint32_t)c;
-                        const int slot = atomicAdd(db.n_refined + f, 1);
-                        if (slot < db.cap_r) db.refined[(size_t)f * db.cap_r + slot] = rec;
-                    }
+                    const int slot = atomicAdd(db.n_cand + f, 1);
+                    if (slot < db.cap_c)
+                        db.cand[(size_t)f * db.cap_c + slot] = ((uint32_t)o << 27) | ((uint32_t)(layer0 - 1) << 26) | ((uint32_t)(y - 1) << 13) | (uint32_t)c;
                 }
             }
         }
 #pragma unroll
         for (int l = 0; l < 4; ++l) { hmaxA[l] = hmaxB[l]; hminA[l] = hminB[l]; hmaxB[l] = hmaxC[l]; hminB[l] = hminC[l]; }
-        cenB[0] = cenC[0]; cenB[1] = cenC[1];
+        cenB[0] = v[1]; cenB[1] = v[2];
+    }
+}
+
+// adjustLocalExtrema for every candidate: thread per candidate, survivors appended as 32-byte records.
+__global__ void __launch_bounds__(128) refine_kernel(const __grid_constant__ PyrView pv, const DetectBuf db) {
+    const int f = blockIdx.y;
+    int n = db.n_cand[f];
+    if (n > db.cap_c) n = db.cap_c;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t key = db.cand[(size_t)f * db.cap_c + i];
+        const int o = key >> 27, layer0 = ((key >> 26) & 1) + 1, r = (key >> 13) & 8191, c = key & 8191;
+        const OctaveView& ov = pv.oct[o];
+        const size_t foff = (size_t)f * ov.frame_stride;
+        const float* D[4] = {ov.D[0] + foff, ov.D[1] + foff, ov.D[2] + foff, ov.D[3] + foff};
+        int r1 = r, c1 = c, layer = layer0;
+        Refined rec;
+        if (!adjust_local_extrema(D, ov.rows, ov.cols, ov.pitch, o, layer, r1, c1, rec)) continue;
+        rec.key = key;
+        const int slot = atomicAdd(db.n_refined + f, 1);
+        if (slot < db.cap_r) db.refined[(size_t)f * db.cap_r + slot] = rec;
     }
 }
 
@@ -217,22 +233,29 @@ __global__ void __launch_bounds__(ORI_WARPS * 32) orientation_kernel(const __gri
         float* priv = s_priv[warp] + lane;
 #pragma unroll
         for (int b = 0; b < kOriBins; ++b) priv[b * 32] = 0.f;
+        // window (2*radius+1)^2 in raster order; rows/cols outside 0 < y < rows-1, 0 < x < cols-1 are skipped (:405,410)
         const int w = 2 * radius + 1;
-        for (int idx = lane; idx < w * w; idx += 32) {
-            const int ii = idx / w - radius, jj = idx % w - radius;
-            const int y = py + ii, x = px + jj;
-            if (y <= 0 || y >= rows - 1 || x <= 0 || x >= cols - 1) continue;
-            const float* q = img + (size_t)y * pitch + x;
-            const float dx = __ldg(q + 1) - __ldg(q - 1);
-            const float dy = __ldg(q - pitch) - __ldg(q + pitch);
-            const float wgt = expf((ii * ii + jj * jj) * expf_scale);
-            const float ori = fast_atan2_deg(dy, dx);
-            const float mag = sqrtf(dx * dx + dy * dy);
-            int bin = cv_round((kOriBins / 360.f) * ori);
-            if (bin >= kOriBins) bin -= kOriBins;
-            if (bin < 0) bin += kOriBins;
-            priv[bin * 32] += wgt * mag;
+        const int i_lo = max(-radius, 1 - py), i_hi = min(radius, rows - 2 - py);
+        const int j_lo = max(-radius, 1 - px), j_hi = min(radius, cols - 2 - px);
+        const int wj = j_hi - j_lo + 1;
+        if (wj > 0) {
+            int ii = i_lo + lane / wj, jj = j_lo + lane % wj;  // flat raster index advanced by 32 without divisions
+            for (; ii <= i_hi; ) {
+                const float* q = img + (size_t)(py + ii) * pitch + (px + jj);
+                const float dx = __ldg(q + 1) - __ldg(q - 1);
+                const float dy = __ldg(q - pitch) - __ldg(q + pitch);
+                const float wgt = expf((ii * ii + jj * jj) * expf_scale);
+                const float ori = fast_atan2_deg(dy, dx);
+                const float mag = sqrtf(dx * dx + dy * dy);
+                int bin = cv_round((kOriBins / 360.f) * ori);
+                if (bin >= kOriBins) bin -= kOriBins;
+                if (bin < 0) bin += kOriBins;
+                priv[bin * 32] += wgt * mag;
+                jj += 32;
+                while (jj > j_hi) { jj -= wj; ++ii; }
+            }
         }
+        (void)w;
         __syncwarp();
         for (int b = lane; b < kOriBins; b += 32) {  // rotated read: lane b starts at copy b, all banks distinct
             float acc = 0.f;
@@ -350,7 +373,12 @@ __global__ void __launch_bounds__(SORT_THREADS) order_scan_kernel(const DetectBu
         if (tid == SORT_THREADS - 1) s_carry = carry + s_warp[31];
         __syncthreads();
     }
-    if (tid == 0) counts_out[f] = s_carry;
+    if (tid == 0) {
+        int total = s_carry;
+        // a full candidate / refined list means keypoints were dropped: report a count above any admissible cap
+        if (db.n_refined[f] > db.cap_r || db.n_cand[f] > db.cap_c) total = max(total, db.cap_r + 1);
+        counts_out[f] = total;
+    }
 }
 
 }  // namespace
@@ -359,9 +387,11 @@ void init_detect_kernels() { cudaFuncSetAttribute(order_scan_kernel, cudaFuncAtt
 
 int launch_extrema(const PyrView& pv, const DetectBuf& db, int n_frames, cudaStream_t st) {
     cudaMemsetAsync(db.n_refined, 0, sizeof(int) * n_frames, st);
+    cudaMemsetAsync(db.n_cand, 0, sizeof(int) * n_frames, st);
     dim3 grid((pv.total_tiles + EX_WARPS - 1) / EX_WARPS, n_frames);
     extrema_kernel<<<grid, EX_WARPS * 32, 0, st>>>(pv, db);
-    return 1;
+    refine_kernel<<<dim3(48, n_frames), 128, 0, st>>>(pv, db);
+    return 2;
 }
 
 int launch_orientation(const PyrView& pv, const DetectBuf& db, int n_frames, cudaStream_t st) {

@@ -47,6 +47,9 @@ struct Refined {
 };
 
 struct DetectBuf {
+    uint32_t* cand;      // [F][cap_c] scan-order keys of the 27-neighbour extrema (before refinement)
+    int* n_cand;         // [F]
+    int cap_c;
     Refined* refined;    // [F][cap_r]
     int* n_refined;      // [F]  (atomic counters, may exceed cap_r)
     float* angles;       // [F][cap_r][kMaxPeaks]
