@@ -508,7 +508,6 @@ int sift_b200_cal_descriptor(SiftB200* h, const float* gpyr, int rows, int cols,
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     cudaFree(d_k); cudaFree(d_d); cudaFree(d_err);
     CUDA_TRY(cudaGetLastError());
-    if (err == 2) return fail(SIFT_B200_ERR_ARG, "keypoint scale too large: descriptor window radius exceeds 40 px (scl_octv > 3.8)");
     if (err) return fail(SIFT_B200_ERR_ASSERT, "octave >= firstOctave && layer <= nOctaveLayers+2 (src/sift.cpp:744)");
     return SIFT_B200_OK;
 }

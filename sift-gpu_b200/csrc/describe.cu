@@ -4,18 +4,20 @@
 // Compiled with --fmad=false so the sample arithmetic (rotation, bins, trilinear weights) rounds like the
 // CPU expression order.
 //
-// The reference scatters every window sample into a (4+2)x(4+2)x(8+2) histogram.  A scatter needs shared-memory
-// float atomics, which on sm_100a are CAS loops (ATOMS.CAST.SPIN) that serialise badly because neighbouring
-// samples hit the same bins.  So the kernel is an atomics-free, deterministic two-phase gather, one CTA (128
-// threads) per keypoint:
-//   phase 1  every window position (raster order, coalesced row loads of the Gaussian level) is evaluated ONCE:
-//            gradient, fastAtan2, magnitude, Gaussian weight -> shared staging {mag*w, obin} (0 when rejected);
-//   phase 2  thread = (cell of the 4x4 grid, row slot): walks the rows of its cell's support (|rbin-a|<1,
-//            |cbin-b|<1, a rotated square; per row the j-interval comes from the two slab inequalities) and
-//            accumulates its trilinear share into a thread-private 9-bin orientation histogram in shared memory
-//            (layout [bin][thread]: conflict-free, plain read-modify-write);
-//   tail     128 threads = 128 output elements: sum the 8 row-slot partials, fold the circular bin, then
-//            L2 -> clamp 0.2 -> x512 -> uchar (round half even) -> L1 -> sqrt with block reductions.
+// The reference scatters every window sample into a (4+2)x(4+2)x(8+2) histogram.  A scatter into one shared histogram
+// needs shared-memory float atomics, which on sm_100a are CAS loops (ATOMS.CAST.SPIN) that serialise badly because
+// neighbouring samples hit the same bins.  This kernel is atomics-free and deterministic, one CTA (128 threads) per
+// keypoint, one pass:
+//   - the 4 cell-rows of the descriptor grid are split in two pairs p (a in {2p, 2p+1}); an 8-lane group owns (pair, window
+//     row): its lanes walk the row's j-interval 2p-1 <= rbin < 2p+2, -1 < cbin < 4 (two slab inequalities, widened by a
+//     pixel; the reference's exact test decides), two samples per lane per step so 8 independent gradient loads are in
+//     flight; lanes of a group read consecutive pixels (coalesced 32-byte segments);
+//   - each sample is evaluated in place (gradient, fastAtan2, magnitude, Gaussian weight -- in the reference's operation
+//     order) and its trilinear votes that fall into the pair's cells go straight into THREAD-PRIVATE histograms
+//     [2 cell-rows][4 cells][9 bins] in shared memory (layout [bin][thread]: conflict-free plain read-modify-write).
+//     A sample is evaluated 1.2 times on average (twice only when its two cell-rows straddle the pairs);
+//   - tail: 128 threads = 128 output elements: sum the 64 private copies of the owning pair (rotated, conflict-free),
+//     fold the circular bin, then L2 -> clamp 0.2 -> x512 -> uchar (round half even) -> L1 -> sqrt with block reductions.
 // Only the inner 4x4 cells are kept by the reference (:676-684), so the border cells are never formed.
 #include "sift_internal.cuh"
 
@@ -24,12 +26,9 @@ namespace {
 
 constexpr int DW = 4, DB = 8;  // SIFT_DESCR_WIDTH, SIFT_DESCR_HIST_BINS (src/sift.cpp:12,15)
 constexpr int DT = 128;        // threads per CTA = output elements
-constexpr int MAXR = 40;       // radius = cvRound(3*scl*sqrt2*2.5), scl_octv < 3.81  
-constexpr int MAXW = 2 * MAXR + 1;
-constexpr int SLOTS = DT / 16; // row slots per cell
-constexpr int SMALL_R = 28;     // radius class boundary (most layer-1 keypoints)
-__host__ __device__ constexpr int desc_smem_bytes(int r) { return (2 * (2 * r + 1) * (2 * r + 1) + (DB + 1) * DT + 8) * 4; }
-constexpr int DESC_SMEM_BYTES = desc_smem_bytes(MAXR);
+constexpr int PRIV_BINS = 2 * DW * (DB + 1);      // private histogram of one thread: [2 cell-rows][4 cells][9 bins]
+constexpr int PRIV_FLOATS = PRIV_BINS * DT;
+constexpr int DESC_SMEM_BYTES = (PRIV_FLOATS + 8) * 4;
 
 __device__ __forceinline__ int cv_round(float v) { return __float2int_rn(v); }
 __device__ __forceinline__ int cv_floor(float v) { return __float2int_rd(v); }
@@ -79,12 +78,9 @@ __device__ __forceinline__ bool slab(float k, float inv_k, float off, float lo_v
     return off > lo_v - 0.01f && off < hi_v + 0.01f;  // k ~ 0: the row is inside or outside as a whole
 }
 
-struct Sample { float mw, ob; };
-
 // calcSIFTDescriptor, src/sift.cpp:579-722, for one keypoint by one CTA.  dst: 128 floats in global memory.
-// wmax: row pitch of the staging arrays (>= 2*radius+1).
-__device__ void calc_descriptor(const float* __restrict__ img, int rows, int cols, int pitch, float ptx, float pty, float ori, float scl, int radius,
-                                int wmax, float* __restrict__ smem, float* __restrict__ dst) {
+__device__ void calc_descriptor(const float* __restrict__ img, int rows, int cols, int pitch, float ptx, float pty, float ori, float scl,
+                                float* __restrict__ smem, float* __restrict__ dst) {
     const int tid = threadIdx.x;
     const int px = cv_round(ptx), py = cv_round(pty);
     float cos_t = cosf(ori * (float)(3.1415926535897932384626433832795 / 180));
@@ -92,34 +88,29 @@ __device__ void calc_descriptor(const float* __restrict__ img, int rows, int col
     const float bins_per_rad = DB / 360.f;
     const float exp_scale = -1.f / (DW * DW * 0.5f);
     const float hist_width = 3.f * scl;
+    const int radius = descr_radius(scl, rows, cols);
     cos_t /= hist_width;
     sin_t /= hist_width;
-    const int w = wmax;
-    float* s_mag = smem;
-    float* s_ob = smem + wmax * wmax;
-    float* s_priv = smem + 2 * wmax * wmax;  // [DB+1][DT]
-    float* s_red = s_priv + (DB + 1) * DT;
+    float* s_priv = smem;  // [PRIV_BINS][DT]
+    float* s_red = smem + PRIV_FLOATS;
     const float inv_s = fabsf(sin_t) > 1e-6f ? 1.f / sin_t : 0.f;
     const float inv_c = fabsf(cos_t) > 1e-6f ? 1.f / cos_t : 0.f;
-    const int jmin = max(-radius, 1 - px), jmax = min(radius, cols - 2 - px);   // 0 < c < cols-1
+    const int jmin = max(-radius, 1 - px), jmax = min(radius, cols - 2 - px);   // 0 < c < cols-1  (:621)
     const int imin = max(-radius, 1 - py), imax = min(radius, rows - 2 - py);   // 0 < r < rows-1
 
-    // ---- phase 1: evaluate every ACCEPTED window sample once.  An 8-lane group owns a window row (16 rows in flight per
-    // CTA); its lanes walk the row's accepted interval -1 < rbin < 4, -1 < cbin < 4 (:620) -- the two slab inequalities in j,
-    // widened by one pixel; the exact reference test decides -- two samples per lane per step so that 8 independent
-    // gradient loads are in flight.  The body is branch-free (rejected samples compute on real pixels and store 0).
-    // Positions outside the interval are never read by phase 2 (its supports lie inside the accepted region).
+    for (int k = tid; k < PRIV_FLOATS; k += DT) s_priv[k] = 0.f;
+    __syncthreads();
     {
         const int gl = tid & 7, grp = tid >> 3;
-        for (int i = imin + grp; i <= imax; i += DT / 8) {
+        const int p = grp & 1, slot = grp >> 1;  // cell-row pair, row slot (8 slots per pair)
+        float* priv = s_priv + tid;
+        for (int i = imin + slot; i <= imax; i += DT / 16) {
             float lo = (float)jmin, hi = (float)jmax;
-            if (!slab(sin_t, inv_s, i * cos_t + 1.5f, -1.f, 4.f, lo, hi)) continue;
+            if (!slab(sin_t, inv_s, i * cos_t + 1.5f, 2 * p - 1.f, 2 * p + 2.f, lo, hi)) continue;
             if (!slab(cos_t, inv_c, -(i * sin_t) + 1.5f, -1.f, 4.f, lo, hi)) continue;
             const int jlo = max(jmin, (int)floorf(lo) - 1);
             const int jhi = min(jmax, (int)ceilf(hi) + 1);
             const float* rowp = img + (size_t)(py + i) * pitch + px;
-            float* mrow = s_mag + (i + radius) * w + radius;
-            float* orow = s_ob + (i + radius) * w + radius;
             const float isin = i * sin_t, icos = i * cos_t;
             for (int j0 = jlo + gl; j0 <= jhi; j0 += 16) {
                 float dxv[2], dyv[2];
@@ -135,85 +126,57 @@ __device__ void calc_descriptor(const float* __restrict__ img, int rows, int col
                     const int j = j0 + 8 * u;
                     const float c_rot = j * cos_t - isin;
                     const float r_rot = j * sin_t + icos;
-                    const float rbin = r_rot + DW / 2 - 0.5f;
-                    const float cbin = c_rot + DW / 2 - 0.5f;
-                    const bool acc = rbin > -1 && rbin < DW && cbin > -1 && cbin < DW;
+                    float rbin = r_rot + DW / 2 - 0.5f;
+                    float cbin = c_rot + DW / 2 - 0.5f;
+                    const bool acc = j <= jhi && rbin > -1 && rbin < DW && cbin > -1 && cbin < DW;  // (:620)
                     const float o_ = fast_atan2_deg(dyv[u], dxv[u]);
                     const float m_ = sqrtf(dxv[u] * dxv[u] + dyv[u] * dyv[u]);
                     const float w_ = expf((c_rot * c_rot + r_rot * r_rot) * exp_scale);
-                    const float ob = (o_ - ori) * bins_per_rad;
-                    const float mw = acc ? m_ * w_ : 0.f;
-                    if (j <= jhi) { mrow[j] = mw; orow[j] = ob; }
+                    float obin = (o_ - ori) * bins_per_rad;
+                    const float mag = m_ * w_;
+                    const int r0 = cv_floor(rbin), c0 = cv_floor(cbin);
+                    int o0 = cv_floor(obin);
+                    rbin -= r0; cbin -= c0; obin -= o0;
+                    if (o0 < 0) o0 += DB;
+                    if (o0 >= DB) o0 -= DB;
+                    const int la = r0 - 2 * p;  // local cell-row of the r0 vote; the r0+1 vote goes to la+1
+                    if (acc && mag != 0.f && la >= -1 && la <= 1) {
+                        // trilinear split in the reference's operation order (:656-662)
+                        const float v_r1 = mag * rbin, v_r0 = mag - v_r1;
+                        const float v_rc11 = v_r1 * cbin, v_rc10 = v_r1 - v_rc11;
+                        const float v_rc01 = v_r0 * cbin, v_rc00 = v_r0 - v_rc01;
+                        float* h = priv + ((la * DW + c0) * (DB + 1) + o0) * DT;
+                        const bool c_lo = c0 >= 0, c_hi = c0 <= DW - 2;
+                        if (la >= 0 && r0 >= 0) {  // cell-row r0 belongs to this pair
+                            if (c_lo) { const float v1 = v_rc00 * obin; h[0] += v_rc00 - v1; h[DT] += v1; }
+                            if (c_hi) { const float v1 = v_rc01 * obin; h[(DB + 1) * DT] += v_rc01 - v1; h[(DB + 2) * DT] += v1; }
+                        }
+                        if (la <= 0 && r0 <= DW - 2) {  // cell-row r0+1 belongs to this pair
+                            float* h1 = h + DW * (DB + 1) * DT;
+                            if (c_lo) { const float v1 = v_rc10 * obin; h1[0] += v_rc10 - v1; h1[DT] += v1; }
+                            if (c_hi) { const float v1 = v_rc11 * obin; h1[(DB + 1) * DT] += v_rc11 - v1; h1[(DB + 2) * DT] += v1; }
+                        }
+                    }
                 }
             }
         }
     }
-#pragma unroll
-    for (int k = 0; k <= DB; ++k) s_priv[k * DT + tid] = 0.f;
     __syncthreads();
 
-    // ---- phase 2: gather.  thread = (cell, row slot) ----
-    {
-        const int cell = tid & 15, slot = tid >> 4;
-        const int a = cell >> 2, b = cell & 3;
-        // cell centre in pixel offsets: rbin = a, cbin = b  <=>  r_rot = a-1.5, c_rot = b-1.5 (units of hist_width)
-        const float ct = cos_t * hist_width, st = sin_t * hist_width;  // ~cos, sin
-        const float rr = (a - 1.5f) * hist_width, cr = (b - 1.5f) * hist_width;
-        const float ic = -cr * st + rr * ct;
-        const float ext = hist_width * (fabsf(ct) + fabsf(st)) + 1.5f;
-        const int ilo = max(imin, (int)ceilf(ic - ext));
-        const int ihi = min(imax, (int)floorf(ic + ext));
-        float* priv = s_priv + tid;
-        for (int i = ilo + slot; i <= ihi; i += SLOTS) {
-            // a-1 <= rbin < a+1 with rbin = j*sin_t + i*cos_t + 1.5 ;  b-1 <= cbin < b+1 with cbin = j*cos_t - i*sin_t + 1.5
-            float lo = (float)jmin, hi = (float)jmax;
-            if (!slab(sin_t, inv_s, i * cos_t + 1.5f, a - 1.f, a + 1.f, lo, hi)) continue;
-            if (!slab(cos_t, inv_c, -(i * sin_t) + 1.5f, b - 1.f, b + 1.f, lo, hi)) continue;
-            const int jlo = max(jmin, (int)floorf(lo) - 1);
-            const int jhi = min(jmax, (int)ceilf(hi) + 1);
-            const int base = (i + radius) * w + radius;
-            for (int j = jlo; j <= jhi; ++j) {
-                const float c_rot = j * cos_t - i * sin_t;
-                const float r_rot = j * sin_t + i * cos_t;
-                float rbin = r_rot + DW / 2 - 0.5f;
-                float cbin = c_rot + DW / 2 - 0.5f;
-                const int r0 = cv_floor(rbin), c0 = cv_floor(cbin);
-                if ((unsigned)(a - r0) > 1u || (unsigned)(b - c0) > 1u) continue;
-                if (!(rbin > -1 && cbin > -1)) continue;  // rbin == -1 exactly is rejected by the reference (:620)
-                const float mag = s_mag[base + j];
-                if (mag == 0.f) continue;  // zero vote: contributes +0
-                float obin = s_ob[base + j];
-                rbin -= r0;
-                cbin -= c0;
-                int o0 = cv_floor(obin);
-                obin -= o0;
-                if (o0 < 0) o0 += DB;
-                if (o0 >= DB) o0 -= DB;
-                // trilinear split in the reference's operation order (:656-662), keeping only this cell's share
-                const float v_r1 = mag * rbin;
-                const float vr = (r0 == a) ? mag - v_r1 : v_r1;
-                const float v_c1 = vr * cbin;
-                const float vrc = (c0 == b) ? vr - v_c1 : v_c1;
-                const float v1 = vrc * obin;
-                const float v0 = vrc - v1;
-                priv[o0 * DT] += v0;
-                priv[(o0 + 1) * DT] += v1;
-            }
-        }
-    }
-    __syncthreads();
-
-    // ---- tail: thread = output element (cell*8 + k) ----
+    // ---- tail: thread = output element (cell*8 + k); its values live in the 64 threads of pair a>>1 ----
     const int e_cell = tid >> 3, e_k = tid & 7;
-    float v = 0.f;
-#pragma unroll
-    for (int g = 0; g < SLOTS; ++g) v += s_priv[e_k * DT + e_cell + 16 * g];
-    if (e_k == 0) {  // hist[idx] += hist[idx+n] (:680); hist[idx+n+1] is never written since o0 <= n-1
-        float f = 0.f;
-#pragma unroll
-        for (int g = 0; g < SLOTS; ++g) f += s_priv[DB * DT + e_cell + 16 * g];
-        v += f;
+    const int e_a = e_cell >> 2, e_b = e_cell & 3;
+    const int e_p = e_a >> 1, e_la = e_a & 1;
+    const float* src_v = s_priv + ((e_la * DW + e_b) * (DB + 1) + e_k) * DT;
+    const float* src_f = s_priv + ((e_la * DW + e_b) * (DB + 1) + DB) * DT;
+    float v = 0.f, fold = 0.f;
+    for (int g = 0; g < DT / 2; ++g) {
+        const int q = (g + tid) & (DT / 2 - 1);            // rotated start: the 32 lanes read 32 different banks
+        const int t = ((q >> 3) * 2 + e_p) * 8 + (q & 7);  // q-th thread of pair e_p: grp = 2*(q>>3)+p, lane q&7
+        v += src_v[t];
+        fold += src_f[t];
     }
+    if (e_k == 0) v += fold;  // hist[idx] += hist[idx+n] (:680); hist[idx+n+1] is never written since o0 <= n-1
     float nrm2 = block_sum(v * v, s_red, tid);
     const float thr = sqrtf(nrm2) * 0.2f;
     v = fminf(v, thr);
@@ -228,9 +191,8 @@ __device__ void calc_descriptor(const float* __restrict__ img, int rows, int col
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(DT, 7)
-    describe_kernel(const __grid_constant__ PyrView pv, const DetectBuf db, SiftKeypoint* __restrict__ kp_out, float* __restrict__ desc_out, int cap,
-                    int r_lo, int r_hi) {  // this launch handles keypoints with r_lo < window radius <= r_hi (staging sized for r_hi)
+__global__ void __launch_bounds__(DT, 6)
+    describe_kernel(const __grid_constant__ PyrView pv, const DetectBuf db, SiftKeypoint* __restrict__ kp_out, float* __restrict__ desc_out, int cap) {
     extern __shared__ float smem[];
     const int f = blockIdx.y;
     int n = db.n_refined[f];
@@ -246,16 +208,13 @@ __global__ void __launch_bounds__(DT, 7)
         const OctaveView& ov = pv.oct[octave];
         const float* img = ov.G[layer] + (size_t)f * ov.frame_stride;
         const float size = rec.size * scale;
-        const int radius = descr_radius(size * 0.5f, ov.rows, ov.cols);
-        if (radius <= r_lo || radius > r_hi) continue;
         for (int k = 0; k < np; ++k) {
             const int slot = base + k;
             if (slot >= cap) break;
             const float kp_angle = db.angles[((size_t)f * db.cap_r + i) * kMaxPeaks + k];
             float angle = 360.f - kp_angle;
             if (fabsf(angle - 360.f) < 1.1920928955078125e-7f) angle = 0.f;
-            calc_descriptor(img, ov.rows, ov.cols, ov.pitch, rec.x * scale, rec.y * scale, angle, size * 0.5f, radius, 2 * r_hi + 1, smem,
-                            desc_out + ((size_t)f * cap + slot) * 128);
+            calc_descriptor(img, ov.rows, ov.cols, ov.pitch, rec.x * scale, rec.y * scale, angle, size * 0.5f, smem, desc_out + ((size_t)f * cap + slot) * 128);
             if (threadIdx.x == 0) {
                 SiftKeypoint kp;
                 kp.x = rec.x; kp.y = rec.y; kp.size = rec.size; kp.angle = kp_angle; kp.response = rec.response;
@@ -285,12 +244,7 @@ __global__ void __launch_bounds__(DT)
         float angle = 360.f - kp.angle;
         if (fabsf(angle - 360.f) < 1.1920928955078125e-7f) angle = 0.f;
         const float size = kp.size * scale;
-        const int radius = descr_radius(size * 0.5f, ov.rows, ov.cols);
-        if (radius > MAXR) {
-            if (threadIdx.x == 0) atomicExch(err, 2);  // window larger than this kernel's staging (scl_octv > 3.8)
-            continue;
-        }
-        calc_descriptor(ov.G[layer], ov.rows, ov.cols, ov.pitch, kp.x * scale, kp.y * scale, angle, size * 0.5f, radius, MAXW, smem, desc_out + (size_t)p * 128);
+        calc_descriptor(ov.G[layer], ov.rows, ov.cols, ov.pitch, kp.x * scale, kp.y * scale, angle, size * 0.5f, smem, desc_out + (size_t)p * 128);
     }
 }
 
@@ -302,11 +256,9 @@ void init_describe_kernels() {
 }
 
 int launch_describe(const PyrView& pv, const DetectBuf& db, int n_frames, SiftKeypoint* d_kp, float* d_desc, int cap, cudaStream_t st) {
-    // two radius classes so that the common small windows (layer 1: radius <= 28) run at ~2x the occupancy
-    dim3 grid(148 * 4, n_frames);
-    describe_kernel<<<grid, DT, desc_smem_bytes(SMALL_R), st>>>(pv, db, d_kp, d_desc, cap, -1, SMALL_R);
-    describe_kernel<<<grid, DT, desc_smem_bytes(MAXR), st>>>(pv, db, d_kp, d_desc, cap, SMALL_R, MAXR);
-    return 2;
+    dim3 grid(148 * 6, n_frames);
+    describe_kernel<<<grid, DT, DESC_SMEM_BYTES, st>>>(pv, db, d_kp, d_desc, cap);
+    return 1;
 }
 
 int launch_describe_given(const PyrView& pv, const SiftKeypoint* d_kps, int n, float* d_desc, int first_octave, int* d_err, cudaStream_t st) {

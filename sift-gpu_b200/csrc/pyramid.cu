@@ -65,17 +65,43 @@ __device__ __forceinline__ void hpass(const float* __restrict__ sIn, float* __re
     }
 }
 
+// Masked tile load, scalar: thread = (column, row phase); 4-byte loads coalesced along the row.  Used for the base blur
+// (arbitrary source pitch / u8 source).  Zero padding AND the reference's ">= rows-1 / cols-1 reads as zero" (src/sift.cpp:116).
 template <int HALO>
 __device__ __forceinline__ void load_tile(float* __restrict__ sIn, const float* __restrict__ src, const uint8_t* __restrict__ src8, int rows,
                                           int cols, int pitch, int ty0, int tx0, int tid) {
     constexpr int IW = TW + 2 * HALO, IH = TH + 2 * HALO, IP = IW + 1;
-    for (int idx = tid; idx < IW * IH; idx += NT) {
-        const int y = idx / IW, x = idx - y * IW;
-        const int gy = ty0 - HALO + y, gx = tx0 - HALO + x;
+    constexpr int RPP = NT / IW;  // rows per pass
+    const int x = tid % IW, y0 = tid / IW;
+    if (y0 >= RPP) return;
+    const int gx = tx0 - HALO + x;
+    const bool col_ok = gx >= 0 && gx < cols - 1;
+    for (int y = y0; y < IH; y += RPP) {
+        const int gy = ty0 - HALO + y;
         float v = 0.f;
-        // zero padding AND the reference's ">= rows-1 / cols-1 reads as zero" window fetch (src/sift.cpp:116)
-        if (gy >= 0 && gx >= 0 && gy < rows - 1 && gx < cols - 1) v = src8 ? (float)src8[(size_t)gy * pitch + gx] : __ldg(src + (size_t)gy * pitch + gx);
+        if (col_ok && gy >= 0 && gy < rows - 1) v = src8 ? (float)src8[(size_t)gy * pitch + gx] : __ldg(src + (size_t)gy * pitch + gx);
         sIn[y * IP + x] = v;
+    }
+}
+
+// Masked tile load for the octave kernel: 16-byte loads.  The workspace pitch is a multiple of 32 floats and tx0 a multiple
+// of 32, so the window [tx0-20, tx0+52) is float4-aligned; the two extra columns on each side are dropped on the way in.
+__device__ __forceinline__ void load_tile_vec(float* __restrict__ sIn, const float* __restrict__ src, int rows, int cols, int pitch, int ty0, int tx0,
+                                              int tid) {
+    constexpr int HALO = kMaxRadius, IW = TW + 2 * HALO, IH = TH + 2 * HALO, IP = IW + 1;
+    constexpr int Q = (IW + 4) / 4;  // 18 float4 per row
+    for (int idx = tid; idx < IH * Q; idx += NT) {
+        const int y = idx / Q, q = idx - y * Q;
+        const int gy = ty0 - HALO + y, gx4 = tx0 - HALO - 2 + 4 * q;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (gy >= 0 && gy < rows - 1 && gx4 >= 0 && gx4 < pitch) v = __ldg(reinterpret_cast<const float4*>(src + (size_t)gy * pitch + gx4));
+        const float e[4] = {v.x, v.y, v.z, v.w};
+        float* out = sIn + y * IP + 4 * q - 2;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int sx = 4 * q - 2 + k, gx = gx4 + k;
+            if (sx >= 0 && sx < IW) out[k] = (gx >= 0 && gx < cols - 1) ? e[k] : 0.f;
+        }
     }
 }
 
@@ -107,7 +133,7 @@ __global__ void __launch_bounds__(NT, 3) octave_kernel(const OctArgs a) {
     const size_t foff = (size_t)blockIdx.z * a.frame_stride;
     const float* G0 = a.G0 + foff;
 
-    load_tile<OCT_HALO>(sIn, G0, nullptr, a.rows, a.cols, a.pitch, ty0, tx0, tid);
+    load_tile_vec(sIn, G0, a.rows, a.cols, a.pitch, ty0, tx0, tid);
     __syncthreads();
     hpass<4, OCT_HALO>(sIn, sH + H_OFF4, tid);
     hpass<3, OCT_HALO>(sIn, sH + H_OFF3, tid);
