@@ -27,8 +27,10 @@ namespace {
 constexpr int DW = 4, DB = 8;  // SIFT_DESCR_WIDTH, SIFT_DESCR_HIST_BINS (src/sift.cpp:12,15)
 constexpr int DT = 128;        // threads per CTA = output elements
 constexpr int PRIV_BINS = 2 * DW * (DB + 1);      // private histogram of one thread: [2 cell-rows][4 cells][9 bins]
-constexpr int PRIV_FLOATS = PRIV_BINS * DT;
-constexpr int DESC_SMEM_BYTES = (PRIV_FLOATS + 8) * 4;
+constexpr int TRASH = PRIV_BINS;                   // private trash bins that swallow votes for cells outside the pair / the 4x4 grid
+constexpr int PRIV_FLOATS = (PRIV_BINS + 2) * DT;  // + two trash rows (a vote updates bins i and i+1)
+constexpr int NB = 128;                            // window rows per band (intervals of one band live in shared memory)
+constexpr int DESC_SMEM_BYTES = (PRIV_FLOATS + 2 * PRIV_BINS + 8) * 4 + 2 * 2 * NB * 4;
 
 __device__ __forceinline__ int cv_round(float v) { return __float2int_rn(v); }
 __device__ __forceinline__ int cv_floor(float v) { return __float2int_rd(v); }
@@ -91,92 +93,120 @@ __device__ void calc_descriptor(const float* __restrict__ img, int rows, int col
     const int radius = descr_radius(scl, rows, cols);
     cos_t /= hist_width;
     sin_t /= hist_width;
-    float* s_priv = smem;  // [PRIV_BINS][DT]
-    float* s_red = smem + PRIV_FLOATS;
+    float* s_priv = smem;                      // [PRIV_BINS + trash][DT]
+    float* s_sum = smem + PRIV_FLOATS;         // [2 pairs][PRIV_BINS] column sums
+    float* s_red = s_sum + 2 * PRIV_BINS;      // 8 floats
+    int* s_jlo = reinterpret_cast<int*>(s_red + 8);  // [2 pairs][NB]
+    int* s_jhi = s_jlo + 2 * NB;
     const float inv_s = fabsf(sin_t) > 1e-6f ? 1.f / sin_t : 0.f;
     const float inv_c = fabsf(cos_t) > 1e-6f ? 1.f / cos_t : 0.f;
     const int jmin = max(-radius, 1 - px), jmax = min(radius, cols - 2 - px);   // 0 < c < cols-1  (:621)
     const int imin = max(-radius, 1 - py), imax = min(radius, rows - 2 - py);   // 0 < r < rows-1
 
-    for (int k = tid; k < PRIV_FLOATS; k += DT) s_priv[k] = 0.f;
-    __syncthreads();
-    {
-        const int gl = tid & 7, grp = tid >> 3;
-        const int p = grp & 1, slot = grp >> 1;  // cell-row pair, row slot (8 slots per pair)
-        float* priv = s_priv + tid;
-        for (int i = imin + slot; i <= imax; i += DT / 16) {
+    for (int k = tid * 4; k < PRIV_FLOATS; k += DT * 4) *reinterpret_cast<float4*>(s_priv + k) = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int gl = tid & 7, grp = tid >> 3;
+    const int p = grp & 1, slot = grp >> 1;  // cell-row pair, row slot (8 slots per pair)
+    float* priv = s_priv + tid;
+    for (int band0 = imin; band0 <= imax; band0 += NB) {
+        const int nrows = min(NB, imax - band0 + 1);
+        // accepted j-interval of every (pair, row) of the band: 2p-1 <= rbin < 2p+2 and -1 < cbin < 4, widened by a pixel
+        for (int it = tid; it < 2 * nrows; it += DT) {
+            const int pp = it >= nrows, i = band0 + it - pp * nrows;
             float lo = (float)jmin, hi = (float)jmax;
-            if (!slab(sin_t, inv_s, i * cos_t + 1.5f, 2 * p - 1.f, 2 * p + 2.f, lo, hi)) continue;
-            if (!slab(cos_t, inv_c, -(i * sin_t) + 1.5f, -1.f, 4.f, lo, hi)) continue;
-            const int jlo = max(jmin, (int)floorf(lo) - 1);
-            const int jhi = min(jmax, (int)ceilf(hi) + 1);
-            const float* rowp = img + (size_t)(py + i) * pitch + px;
-            const float isin = i * sin_t, icos = i * cos_t;
-            for (int j0 = jlo + gl; j0 <= jhi; j0 += 16) {
-                float dxv[2], dyv[2];
+            bool ok = slab(sin_t, inv_s, i * cos_t + 1.5f, 2 * pp - 1.f, 2 * pp + 2.f, lo, hi);
+            ok = ok && slab(cos_t, inv_c, -(i * sin_t) + 1.5f, -1.f, 4.f, lo, hi);
+            s_jlo[pp * NB + it - pp * nrows] = ok ? max(jmin, (int)floorf(lo) - 1) : 1;
+            s_jhi[pp * NB + it - pp * nrows] = ok ? min(jmax, (int)ceilf(hi) + 1) : 0;
+        }
+        __syncthreads();
+        // flattened walk: a group advances through its rows (slot, slot+8, ...) one 16-sample step per iteration, so the four
+        // groups of a warp never wait for each other at row boundaries
+        int r = slot - DT / 16, jb = 1, jhi = 0;
+        const float* rowp = img;
+        float isin = 0.f, icos = 0.f;
+        for (;;) {
+            if (jb > jhi) {
+                do {
+                    r += DT / 16;
+                    if (r >= nrows) break;
+                    jb = s_jlo[p * NB + r];
+                    jhi = s_jhi[p * NB + r];
+                } while (jb > jhi);
+                if (r >= nrows) break;
+                const int i = band0 + r;
+                rowp = img + (size_t)(py + i) * pitch + px;
+                isin = i * sin_t;
+                icos = i * cos_t;
+            }
+            const int j0 = jb + gl;
+            jb += 16;
+            float dxv[2], dyv[2];
 #pragma unroll
-                for (int u = 0; u < 2; ++u) {
-                    const int j = min(j0 + 8 * u, jmax);  // clamped: always an interior pixel, loads are unconditional
-                    const float* q = rowp + j;
-                    dxv[u] = __ldg(q + 1) - __ldg(q - 1);
-                    dyv[u] = __ldg(q - pitch) - __ldg(q + pitch);
-                }
+            for (int u = 0; u < 2; ++u) {
+                const int j = min(j0 + 8 * u, jmax);  // clamped: always an interior pixel, loads are unconditional
+                const float* q = rowp + j;
+                dxv[u] = __ldg(q + 1) - __ldg(q - 1);
+                dyv[u] = __ldg(q - pitch) - __ldg(q + pitch);
+            }
 #pragma unroll
-                for (int u = 0; u < 2; ++u) {
-                    const int j = j0 + 8 * u;
-                    const float c_rot = j * cos_t - isin;
-                    const float r_rot = j * sin_t + icos;
-                    float rbin = r_rot + DW / 2 - 0.5f;
-                    float cbin = c_rot + DW / 2 - 0.5f;
-                    const bool acc = j <= jhi && rbin > -1 && rbin < DW && cbin > -1 && cbin < DW;  // (:620)
-                    const float o_ = fast_atan2_deg(dyv[u], dxv[u]);
-                    const float m_ = sqrtf(dxv[u] * dxv[u] + dyv[u] * dyv[u]);
-                    const float w_ = expf((c_rot * c_rot + r_rot * r_rot) * exp_scale);
-                    float obin = (o_ - ori) * bins_per_rad;
-                    const float mag = m_ * w_;
-                    const int r0 = cv_floor(rbin), c0 = cv_floor(cbin);
-                    int o0 = cv_floor(obin);
-                    rbin -= r0; cbin -= c0; obin -= o0;
-                    if (o0 < 0) o0 += DB;
-                    if (o0 >= DB) o0 -= DB;
-                    const int la = r0 - 2 * p;  // local cell-row of the r0 vote; the r0+1 vote goes to la+1
-                    if (acc && mag != 0.f && la >= -1 && la <= 1) {
-                        // trilinear split in the reference's operation order (:656-662)
-                        const float v_r1 = mag * rbin, v_r0 = mag - v_r1;
-                        const float v_rc11 = v_r1 * cbin, v_rc10 = v_r1 - v_rc11;
-                        const float v_rc01 = v_r0 * cbin, v_rc00 = v_r0 - v_rc01;
-                        float* h = priv + ((la * DW + c0) * (DB + 1) + o0) * DT;
-                        const bool c_lo = c0 >= 0, c_hi = c0 <= DW - 2;
-                        if (la >= 0 && r0 >= 0) {  // cell-row r0 belongs to this pair
-                            if (c_lo) { const float v1 = v_rc00 * obin; h[0] += v_rc00 - v1; h[DT] += v1; }
-                            if (c_hi) { const float v1 = v_rc01 * obin; h[(DB + 1) * DT] += v_rc01 - v1; h[(DB + 2) * DT] += v1; }
-                        }
-                        if (la <= 0 && r0 <= DW - 2) {  // cell-row r0+1 belongs to this pair
-                            float* h1 = h + DW * (DB + 1) * DT;
-                            if (c_lo) { const float v1 = v_rc10 * obin; h1[0] += v_rc10 - v1; h1[DT] += v1; }
-                            if (c_hi) { const float v1 = v_rc11 * obin; h1[(DB + 1) * DT] += v_rc11 - v1; h1[(DB + 2) * DT] += v1; }
-                        }
-                    }
+            for (int u = 0; u < 2; ++u) {
+                const int j = j0 + 8 * u;
+                const float c_rot = j * cos_t - isin;
+                const float r_rot = j * sin_t + icos;
+                float rbin = r_rot + DW / 2 - 0.5f;
+                float cbin = c_rot + DW / 2 - 0.5f;
+                const bool acc = j <= jhi && rbin > -1 && rbin < DW && cbin > -1 && cbin < DW;  // (:620)
+                const float o_ = fast_atan2_deg(dyv[u], dxv[u]);
+                const float m_ = sqrtf(dxv[u] * dxv[u] + dyv[u] * dyv[u]);
+                const float w_ = expf((c_rot * c_rot + r_rot * r_rot) * exp_scale);
+                float obin = (o_ - ori) * bins_per_rad;
+                const float mag = m_ * w_;
+                const int r0 = cv_floor(rbin), c0 = cv_floor(cbin);
+                int o0 = cv_floor(obin);
+                rbin -= r0; cbin -= c0; obin -= o0;
+                if (o0 < 0) o0 += DB;
+                if (o0 >= DB) o0 -= DB;
+                const int la = r0 - 2 * p;  // local cell-row of the r0 vote; the r0+1 vote goes to la+1
+                if (acc && mag != 0.f && la >= -1 && la <= 1) {
+                    // trilinear split in the reference's operation order (:656-662); votes for cells outside this pair or
+                    // outside the 4x4 grid land in the thread's trash bin, so the eight updates are branch-free
+                    const float v_r1 = mag * rbin, v_r0 = mag - v_r1;
+                    const float v_rc11 = v_r1 * cbin, v_rc10 = v_r1 - v_rc11;
+                    const float v_rc01 = v_r0 * cbin, v_rc00 = v_r0 - v_rc01;
+                    const bool r_lo = la >= 0, r_hi = la <= 0, c_lo = c0 >= 0, c_hi = c0 <= DW - 2;
+                    const int b00 = (la * DW + c0) * (DB + 1) + o0;  // bin of (r0, c0, o0)
+                    const int i00 = r_lo && c_lo ? b00 : TRASH, i01 = r_lo && c_hi ? b00 + (DB + 1) : TRASH;
+                    const int i10 = r_hi && c_lo ? b00 + DW * (DB + 1) : TRASH, i11 = r_hi && c_hi ? b00 + (DW + 1) * (DB + 1) : TRASH;
+                    float v1;
+                    v1 = v_rc00 * obin; priv[i00 * DT] += v_rc00 - v1; priv[(i00 + 1) * DT] += v1;
+                    v1 = v_rc01 * obin; priv[i01 * DT] += v_rc01 - v1; priv[(i01 + 1) * DT] += v1;
+                    v1 = v_rc10 * obin; priv[i10 * DT] += v_rc10 - v1; priv[(i10 + 1) * DT] += v1;
+                    v1 = v_rc11 * obin; priv[i11 * DT] += v_rc11 - v1; priv[(i11 + 1) * DT] += v1;
                 }
             }
         }
+        __syncthreads();
+    }
+
+    // ---- tail, stage A: the 2 x 72 column sums over the 64 private copies of each pair (rotated read: conflict-free) ----
+    for (int sidx = tid; sidx < 2 * PRIV_BINS; sidx += DT) {
+        const int sp = sidx >= PRIV_BINS, bin = sidx - sp * PRIV_BINS;
+        const float* col = s_priv + bin * DT + sp * 8;
+        float acc = 0.f;
+#pragma unroll 8
+        for (int g = 0; g < DT / 2; ++g) {
+            const int q = (g + tid) & (DT / 2 - 1);
+            acc += col[(q >> 3) * 16 + (q & 7)];  // q-th thread of pair sp: grp = 2*(q>>3)+sp, lane q&7
+        }
+        s_sum[sidx] = acc;
     }
     __syncthreads();
-
-    // ---- tail: thread = output element (cell*8 + k); its values live in the 64 threads of pair a>>1 ----
+    // ---- stage B: thread = output element (cell*8 + k) ----
     const int e_cell = tid >> 3, e_k = tid & 7;
     const int e_a = e_cell >> 2, e_b = e_cell & 3;
-    const int e_p = e_a >> 1, e_la = e_a & 1;
-    const float* src_v = s_priv + ((e_la * DW + e_b) * (DB + 1) + e_k) * DT;
-    const float* src_f = s_priv + ((e_la * DW + e_b) * (DB + 1) + DB) * DT;
-    float v = 0.f, fold = 0.f;
-    for (int g = 0; g < DT / 2; ++g) {
-        const int q = (g + tid) & (DT / 2 - 1);            // rotated start: the 32 lanes read 32 different banks
-        const int t = ((q >> 3) * 2 + e_p) * 8 + (q & 7);  // q-th thread of pair e_p: grp = 2*(q>>3)+p, lane q&7
-        v += src_v[t];
-        fold += src_f[t];
-    }
-    if (e_k == 0) v += fold;  // hist[idx] += hist[idx+n] (:680); hist[idx+n+1] is never written since o0 <= n-1
+    const float* ssum = s_sum + (e_a >> 1) * PRIV_BINS + ((e_a & 1) * DW + e_b) * (DB + 1);
+    float v = ssum[e_k];
+    if (e_k == 0) v += ssum[DB];  // hist[idx] += hist[idx+n] (:680); hist[idx+n+1] is never written since o0 <= n-1
     float nrm2 = block_sum(v * v, s_red, tid);
     const float thr = sqrtf(nrm2) * 0.2f;
     v = fminf(v, thr);
