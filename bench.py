@@ -174,6 +174,7 @@ def cpu_reference_run(steps: int, warmup: int, budget_s: float):
     frame = make_frames(1)[0]
     if O.have_ref():
         kind, impl = "reference", O.ref()
+        impl.set_threads(os.cpu_count() or 1)  # torchrun exports OMP_NUM_THREADS=1; the reference uses all cores (:738)
         cores = impl.omp_max_threads()
         full_s = 21.0  # ~10 us per pixel on a 2-3 GHz core (direct 2-D blur, src/sift.cpp:137-149)
         run = lambda img: impl.sift_ncl(img)
@@ -205,7 +206,7 @@ def cpu_reference_run(steps: int, warmup: int, budget_s: float):
     return {"value": frac / t, "unit": "frames/s", "cores": cores, "kind": kind, "sample": sample}, t
 
 
-def run_reference(args):
+def run_reference(args, out):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
@@ -215,12 +216,12 @@ def run_reference(args):
             "data": "synthetic", "config": {"workload": WORKLOAD, "note": "CPU arm: one process, host cores only, no GPU"},
             "cpu_baseline": base, "e2e": {"value": base["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    out.emit(json.dumps(line))
     return 0
 
 
 # ---- our arm --------------------------------------------------------------------------------------------------
-def run_ours(args):
+def run_ours(args, out):
     import torch
     import torch.distributed as dist
 
@@ -352,11 +353,31 @@ def run_ours(args):
                            "l2": f"inputs larger than L2: {B} frames x 8.3 MB per step, workspace {chunk} x 77 MB"},
                 "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "roofline_by_kernel": by_kernel,
                 "roofline_pipeline": roofline_pipeline, "cpu_baseline": cpu_base}
-        print(json.dumps(line))
+        out.emit(json.dumps(line))
     s.close()
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+class CleanStdout:
+    """Route fd 1 to stderr while the benchmark runs (NCCL and the reference print banners/timers on stdout) and keep the
+    real stdout for the single JSON line."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.real = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def emit(self, line: str):
+        sys.stdout.flush()
+        os.write(self.real, (line + "\n").encode())
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.real, 1)
+        os.close(self.real)
 
 
 def main():
@@ -377,7 +398,8 @@ def main():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
                "--master-port", "29517", os.path.abspath(__file__)] + sys.argv[1:]
         return subprocess.call(cmd)
-    return run_reference(args) if args.impl == "reference" else run_ours(args)
+    with CleanStdout() as out:
+        return run_reference(args, out) if args.impl == "reference" else run_ours(args, out)
 
 
 if __name__ == "__main__":

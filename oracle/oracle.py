@@ -219,6 +219,9 @@ class _Ref:
     def omp_max_threads(self) -> int:
         return int(self.lib.ref_omp_max_threads())
 
+    def set_threads(self, n: int) -> None:
+        self.lib.ref_set_threads(C.c_int(int(n)))
+
     def gaussian_blur(self, src, sigma, one_d=False):
         src = np.ascontiguousarray(src, dtype=np.float32)
         dst = np.empty_like(src)

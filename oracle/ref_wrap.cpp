@@ -109,4 +109,6 @@ int ref_sift_ncl(const float* image, int rows, int cols, OracleKeypoint* kp_out,
     return rc;
 }
 int ref_omp_max_threads(void) { return omp_get_max_threads(); }
+/* torchrun exports OMP_NUM_THREADS=1; the reference itself would use every core in calDescriptor (src/sift.cpp:738) */
+void ref_set_threads(int n) { omp_set_num_threads(n < 1 ? 1 : n); }
 }
