@@ -85,6 +85,14 @@ int sift_b200_detect_describe_batch_host(SiftB200* h, const float* imgs, int n_f
 int sift_b200_detect_describe_batch_dev_u8(SiftB200* h, const uint8_t* d_imgs, int n_frames, int rows, int cols,
                                            SiftKeypoint* d_kp, float* d_desc, int* d_counts, int cap, void* stream);
 
+/* 2x bilinear upsample front end (BASELINE config 3; the reference ignores doubleSize, src/sift.cpp:219-227, so this is an
+ * extension with cv::resize(INTER_LINEAR) semantics: half-pixel centres, edge replicate).
+ * Device: d_src [n_frames][rows][cols] -> d_dst [n_frames][2*rows][2*cols], asynchronous on `stream`; feed d_dst to
+ * sift_b200_detect_describe_batch_dev.  Host: one image, upsample + SIFT_NCL; keypoint coordinates are in UPSAMPLED pixels. */
+int sift_b200_upsample2x_dev(SiftB200* h, const float* d_src, int n_frames, int rows, int cols, float* d_dst, void* stream);
+int sift_b200_detect_describe_up2(SiftB200* h, const float* img, int rows, int cols, SiftKeypoint* kp_out, float* desc_out, int cap,
+                                  int* n_out, float* upsampled_out /* optional 2rows x 2cols host copy */);
+
 /* ---- sub-modules (include/sift.hpp:47-67), host buffers, synchronous ---------------------------- */
 
 /* Gaussian_Blur (include/sift.hpp:47, src/sift.cpp:123-153): unnormalised truncated 2-D Gaussian,

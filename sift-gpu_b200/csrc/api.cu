@@ -379,6 +379,42 @@ int sift_b200_detect_describe(SiftB200* h, const float* img, int rows, int cols,
     return status;
 }
 
+int sift_b200_upsample2x_dev(SiftB200* h, const float* d_src, int n_frames, int rows, int cols, float* d_dst, void* stream) {
+    if (!h || !d_src || !d_dst || rows < 1 || cols < 1 || n_frames < 0) return fail(SIFT_B200_ERR_ARG, "bad argument");
+    CUDA_TRY(cudaSetDevice(h->device));
+    h->launches += launch_upsample2x(d_src, d_dst, rows, cols, n_frames, (cudaStream_t)stream);
+    CUDA_TRY(cudaGetLastError());
+    return SIFT_B200_OK;
+}
+
+int sift_b200_detect_describe_up2(SiftB200* h, const float* img, int rows, int cols, SiftKeypoint* kp_out, float* desc_out, int cap, int* n_out,
+                                  float* upsampled_out) {
+    int rc = check_dims(h, 2 * rows, 2 * cols);
+    if (rc) return rc;
+    if (!img || !kp_out || !desc_out || !n_out) return fail(SIFT_B200_ERR_ARG, "null buffer");
+    CUDA_TRY(cudaSetDevice(h->device));
+    if ((rc = ensure_staging(h))) return rc;
+    float* d_src = nullptr;
+    CUDA_TRY(cudaMalloc((void**)&d_src, (size_t)rows * cols * 4));
+    CUDA_TRY(cudaMemcpyAsync(d_src, img, (size_t)rows * cols * 4, cudaMemcpyHostToDevice, h->stream));
+    h->launches += launch_upsample2x(d_src, h->d_img, rows, cols, 1, h->stream);
+    if (upsampled_out) CUDA_TRY(cudaMemcpyAsync(upsampled_out, h->d_img, (size_t)rows * cols * 16, cudaMemcpyDeviceToHost, h->stream));
+    rc = run_pipeline(h, h->d_img, nullptr, 1, 2 * rows, 2 * cols, h->d_kp, h->d_desc, h->d_counts, cap, h->stream);
+    if (rc) { cudaFree(d_src); return rc; }
+    CUDA_TRY(cudaMemcpyAsync(h->h_counts, h->d_counts, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    cudaFree(d_src);
+    int n = h->h_counts[0];
+    *n_out = n;
+    int status = SIFT_B200_OK;
+    if (n > cap) { n = cap; status = fail(SIFT_B200_ERR_CAPACITY, "keypoint capacity exceeded: outputs truncated"); }
+    if (n > 0) {
+        CUDA_TRY(cudaMemcpy(kp_out, h->d_kp, n * sizeof(SiftKeypoint), cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpy(desc_out, h->d_desc, (size_t)n * 128 * sizeof(float), cudaMemcpyDeviceToHost));
+    }
+    return status;
+}
+
 // ---- sub-modules --------------------------------------------------------------------------------------------
 
 static int blur_any(SiftB200* h, const float* src, int rows, int cols, double sigma_d, float* dst, bool one_d) {

@@ -228,6 +228,28 @@ __global__ void blur_pass_kernel(const float* __restrict__ src, float* __restric
     dst[(size_t)y * cols + x] = acc;
 }
 
+// ---- 2x bilinear upsample (BASELINE config 3: "2x upsampled base octave") ------------------------------------------
+// The reference has no upsample path (createInitialImage ignores doubleSize, src/sift.cpp:219-227); this is the front end the
+// north star names, with cv::resize(INTER_LINEAR) semantics: half-pixel centres, sx = floor(x/2 - 0.25), weights 0.25/0.75,
+// edge replicate (fx = 0 at sx < 0 and sx >= cols-1).  Horizontal pass then vertical pass, mul and add rounded separately.
+__global__ void upsample2x_kernel(const float* __restrict__ src, float* __restrict__ dst, int rows, int cols, size_t src_fs, size_t dst_fs) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= 2 * cols || y >= 2 * rows) return;
+    float fx = (float)((x + 0.5) * 0.5 - 0.5), fy = (float)((y + 0.5) * 0.5 - 0.5);
+    int sx = (int)floorf(fx), sy = (int)floorf(fy);
+    fx -= sx; fy -= sy;
+    if (sx < 0) { sx = 0; fx = 0.f; }
+    if (sx >= cols - 1) { sx = cols - 1; fx = 0.f; }
+    if (sy < 0) { sy = 0; fy = 0.f; }
+    if (sy >= rows - 1) { sy = rows - 1; fy = 0.f; }
+    const int sx1 = min(sx + 1, cols - 1), sy1 = min(sy + 1, rows - 1);
+    const float* s = src + (size_t)blockIdx.z * src_fs;
+    const float a0 = 1.f - fx, a1 = fx, b0 = 1.f - fy, b1 = fy;
+    const float h0 = __fadd_rn(__fmul_rn(__ldg(s + (size_t)sy * cols + sx), a0), __fmul_rn(__ldg(s + (size_t)sy * cols + sx1), a1));
+    const float h1 = __fadd_rn(__fmul_rn(__ldg(s + (size_t)sy1 * cols + sx), a0), __fmul_rn(__ldg(s + (size_t)sy1 * cols + sx1), a1));
+    dst[(size_t)blockIdx.z * dst_fs + (size_t)y * (2 * cols) + x] = __fadd_rn(__fmul_rn(h0, b0), __fmul_rn(h1, b1));
+}
+
 __global__ void dog_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ d, size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) d[i] = b[i] - a[i];
@@ -283,6 +305,12 @@ int launch_generic_blur(const float* src, float* dst, int rows, int cols, const 
     }
     cudaFreeAsync(tmp, st);
     return 2;
+}
+
+int launch_upsample2x(const float* src, float* dst, int rows, int cols, int n_frames, cudaStream_t st) {
+    dim3 blk(32, 8), grid((2 * cols + 31) / 32, (2 * rows + 7) / 8, n_frames);
+    upsample2x_kernel<<<grid, blk, 0, st>>>(src, dst, rows, cols, (size_t)rows * cols, (size_t)rows * cols * 4);
+    return 1;
 }
 
 int launch_dog(const PyrView& pv, int n_frames, cudaStream_t st) {

@@ -31,3 +31,25 @@ def recipe_s(width: int, height: int, seed: int = 1234, blobs_per_1080p: int = 6
         img[y0:y1, x0:x1] += np.float32(a * sg) * g.astype(np.float32)
     img += rng.normal(0.0, 2.0, (height, width)).astype(np.float32)
     return np.clip(img, 0.0, 255.0).astype(np.float32)
+
+
+def upsample2x(img: np.ndarray) -> np.ndarray:
+    """cv::resize(img, 2x, INTER_LINEAR) restated in numpy float32 (half-pixel centres, edge replicate; horizontal then
+    vertical pass, mul and add rounded separately) -- the checker for the GPU upsample front end (BASELINE config 3)."""
+    img = np.asarray(img, dtype=np.float32)
+
+    def taps(n):
+        d = np.arange(2 * n)
+        f = ((d + 0.5) * 0.5 - 0.5).astype(np.float32)
+        s0 = np.floor(f).astype(np.int64)
+        w = (f - s0).astype(np.float32)
+        lo = s0 < 0
+        s0[lo], w[lo] = 0, 0.0
+        hi = s0 >= n - 1
+        s0[hi], w[hi] = n - 1, 0.0
+        return s0, np.minimum(s0 + 1, n - 1), (np.float32(1) - w).astype(np.float32), w
+
+    x0, x1, a0, a1 = taps(img.shape[1])
+    y0, y1, b0, b1 = taps(img.shape[0])
+    h = (img[:, x0] * a0[None, :]).astype(np.float32) + (img[:, x1] * a1[None, :]).astype(np.float32)
+    return ((h[y0] * b0[:, None]).astype(np.float32) + (h[y1] * b1[:, None]).astype(np.float32)).astype(np.float32)

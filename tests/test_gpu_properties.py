@@ -130,3 +130,32 @@ def test_launches_are_counted(pkg, synth):
     s.detect_describe(synth.recipe_s(128, 128, seed=4))
     assert s.launch_count() - n0 == 11  # base blur, 5 octaves, extrema scan, refine, orientation, order+scan, descriptors
     s.close()
+
+
+def test_upsample_front_end_and_config3(pkg, oracle, synth):
+    """BASELINE config 3: synthetic 3840x2160 frame (recipe S, 24 000 blobs), 2x bilinear upsample to 7680x4320, then the
+    unchanged pipeline.  The reference has no upsample path (src/sift.cpp:219-227 ignores doubleSize), so the checker is
+    the numpy restatement of cv::resize(INTER_LINEAR) (tests/test_host_logic.py pins it to cv2) followed by the CPU oracle.
+    Keypoint coordinates are in upsampled pixels."""
+    s = pkg.Sift(4320, 7680, max_batch=1, max_kp_per_frame=1 << 17)
+    small = synth.recipe_s(300, 200, seed=8, blobs_per_1080p=20000)
+    kp, desc, up = s.detect_describe_up2(small, want_upsampled=True)
+    want_up = synth.upsample2x(small)
+    assert np.array_equal(up, want_up)  # separately rounded mul/add: bit-exact against the restatement
+    okp, odesc = oracle.f32().sift_ncl(want_up)
+    pairs = parity.match_keypoints(kp, okp)
+    rec, prec = parity.recall_precision(pairs, len(kp), len(okp))
+    assert len(okp) > 100 and rec >= 0.99 and prec >= 0.99
+    # full size
+    frame = synth.recipe_s(3840, 2160, seed=1234)
+    kp, desc, up = s.detect_describe_up2(frame, want_upsampled=True)
+    want_up = synth.upsample2x(frame)
+    assert up.shape == (4320, 7680) and np.array_equal(up, want_up)
+    okp, odesc, _, _, opq = oracle.f32().sift_ncl(want_up, want_pyramids=True, want_prequant=True)
+    pairs = parity.match_keypoints(kp, okp)
+    rec, prec = parity.recall_precision(pairs, len(kp), len(okp))
+    assert len(okp) > 5000 and rec >= 0.99 and prec >= 0.99, (len(kp), len(okp), rec, prec)
+    pi = np.array([p[0] for p in pairs]); pj = np.array([p[1] for p in pairs])
+    frac, explained, unexplained, mx = parity.descriptor_report(desc[pi], odesc[pj], opq[pj])
+    assert frac >= 0.93 and unexplained <= len(pairs) // 200, (frac, explained, unexplained, mx)
+    s.close()

@@ -73,3 +73,17 @@ def test_two_rank_reduction_gloo(tmp_path):
                         "--master-port", "29533", str(script), root], capture_output=True, text=True, env=env, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert r.stdout.count("ok") == 2
+
+
+def test_upsample2x_restatement_matches_cv2(synth):
+    """The numpy restatement of cv::resize(2x, INTER_LINEAR) used as the checker for the GPU front end (config 3).
+    cv2's SIMD path fuses one multiply-add, so agreement is to 1e-4 on 0..255 data, not bit-exact."""
+    import pytest
+
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(5)
+    for shape in [(37, 53), (120, 200), (5, 4), (2, 2)]:
+        img = (rng.random(shape) * 255).astype(np.float32)
+        got = synth.upsample2x(img)
+        want = cv2.resize(img, (2 * shape[1], 2 * shape[0]), interpolation=cv2.INTER_LINEAR)
+        assert got.shape == want.shape and np.abs(got - want).max() <= 1e-4
