@@ -55,6 +55,7 @@ def algorithmic_bytes_per_frame(n_kp: float, rows=ROWS, cols=COLS):
     per_kernel = {
         "base_blur_kernel": 4 * (P0 + P0),                       # read the frame, write G0 of octave 0
         "octave_kernel": 4 * (sumP + 6 * sumP + (sumP - P0)),    # read G0; write G1,G2,D0..D3; write the next base
+        "gradient_kernel": 0,                                    # implementation choice (gradient maps), not algorithmic traffic
         "extrema_kernel": 4 * 4 * sumP,                          # read D0..D3 once
         "orientation_kernel": 4 * sumP,                          # G1/G2 gathers: half of the "read G1,G2 once" term
         "describe_kernel": 4 * sumP + 540 * n_kp,                # the other half + 28 B keypoint + 512 B descriptor
@@ -294,14 +295,14 @@ def run_ours(args, out):
     stage = s.stage_ms()
     s.set_stage_timing(False)
     last_chunk = B - ((B - 1) // chunk) * chunk
-    names = ["base_blur_kernel", "octave_kernel", "extrema_kernel", "orientation_kernel", "order_scan_kernel", "describe_kernel"]
+    names = ["base_blur_kernel", "octave_kernel", "gradient_kernel", "extrema_kernel", "orientation_kernel", "order_scan_kernel", "describe_kernel"]
     peak, peak_src = load_peaks()
     total_bytes, per_kernel_bytes = algorithmic_bytes_per_frame(n_kp)
     by_kernel = {}
-    for nm, ms in zip(names, stage[:6]):
+    for nm, ms in zip(names, stage[:7]):
         us_frame = ms * 1e3 / last_chunk
         gbs = per_kernel_bytes[nm] / (us_frame * 1e-6) / 1e9 if us_frame > 0 else 0.0
-        by_kernel[nm] = {"us_per_frame": round(us_frame, 3), "share": round(ms / stage[6], 4), "alg_bytes_per_frame": int(per_kernel_bytes[nm]),
+        by_kernel[nm] = {"us_per_frame": round(us_frame, 3), "share": round(ms / stage[7], 4), "alg_bytes_per_frame": int(per_kernel_bytes[nm]),
                          "achieved_gbs": round(gbs, 1), "frac": round(gbs / peak, 4)}
     top = max(names, key=lambda k: by_kernel[k]["us_per_frame"])
     launches_of_top = {"octave_kernel": N_OCT}.get(top, 1)  # launches per chunk

@@ -121,11 +121,11 @@ int sift_b200_match_knn2(SiftB200* h, const float* query, int nq, const float* t
 /* ---- introspection for the benchmark ------------------------------------------------------------ */
 /* Kernel launches issued by this handle since creation (bench.py reports the delta as gpu_launches). */
 long long sift_b200_launch_count(const SiftB200* h);
-/* CUDA-event time (ms) of the last batch_dev call, split by stage: [0] base blur, [1] octave blur+DoG,
- * [2] extrema+refine, [3] orientation, [4] order+scan, [5] descriptors, [6] total.  Only filled when
- * stage timing was enabled with sift_b200_set_stage_timing(h, 1) (adds event records, no syncs). */
+/* CUDA-event time (ms) of the last batch_dev call, split by stage: [0] base blur, [1] octave blur+DoG, [2] gradient maps,
+ * [3] extrema scan + refine, [4] orientation, [5] order+scan, [6] descriptors, [7] total.  Only filled when stage timing was
+ * enabled with sift_b200_set_stage_timing(h, 1) (adds event records, no syncs). */
 int sift_b200_set_stage_timing(SiftB200* h, int on);
-int sift_b200_get_stage_ms(SiftB200* h, float* ms7);
+int sift_b200_get_stage_ms(SiftB200* h, float* ms8);
 
 #ifdef __cplusplus
 }

@@ -210,7 +210,7 @@ class Sift:
         self._check(lib().sift_b200_set_stage_timing(self._h, int(on)))
 
     def stage_ms(self):
-        ms = (C.c_float * 7)()
+        ms = (C.c_float * 8)()
         self._check(lib().sift_b200_get_stage_ms(self._h, ms))
         return list(ms)
 

@@ -51,7 +51,7 @@ struct SiftB200 {
     cudaEvent_t ev_in[2] = {}, ev_comp[2] = {}, ev_cnt[2] = {}, ev_out[2] = {};
     long long launches = 0;
     bool stage_timing = false;
-    cudaEvent_t ev[8] = {};
+    cudaEvent_t ev[9] = {};
     bool ev_valid = false;
 };
 
@@ -71,7 +71,7 @@ int make_view(float* base, int rows, int cols, int n_oct, int n_frames, bool ful
     if (n_oct < 1 || n_oct > kMaxOctaves) return SIFT_B200_ERR_ARG;
     memset(pv, 0, sizeof(*pv));
     pv->n_oct = n_oct;
-    int tiles = 0;
+    int tiles = 0, gtiles = 0;
     float* p = base;
     for (int o = 0; o < n_oct; ++o) {
         if (rows < 1 || cols < 1) return SIFT_B200_ERR_TOO_SMALL;
@@ -83,6 +83,12 @@ int make_view(float* base, int rows, int cols, int n_oct, int n_frames, bool ful
             if (i < 3 || full) { v.G[i] = p; p += lvl; } else v.G[i] = nullptr;
         }
         for (int i = 0; i < kNumScales - 1; ++i) { v.D[i] = p; p += lvl; }
+        for (int i = 0; i < kNumScales; ++i) {
+            if (i == 1 || i == 2 || full) { v.MO[i] = reinterpret_cast<float2*>(p); p += 2 * lvl; } else v.MO[i] = nullptr;
+        }
+        v.grad_tiles_x = (cols + 31) / 32;
+        v.grad_tile_base = gtiles;
+        gtiles += v.grad_tiles_x * ((rows + 7) / 8);
         // extrema strips: 30 x 16 outputs over the interior [5, rows-5) x [5, cols-5)  (detect.cu)
         const int in_c = cols - 2 * kImgBorder, in_r = rows - 2 * kImgBorder;
         v.tiles_x = in_c > 0 ? (in_c + 29) / 30 : 0;
@@ -91,6 +97,7 @@ int make_view(float* base, int rows, int cols, int n_oct, int n_frames, bool ful
         rows /= 2; cols /= 2;
     }
     pv->total_tiles = tiles;
+    pv->total_grad_tiles = gtiles;
     return SIFT_B200_OK;
 }
 
@@ -117,7 +124,7 @@ void pipeline_sigmas(float sig[5]) {
 }
 
 int ensure_full(SiftB200* h, int rows, int cols, int n_oct) {
-    const size_t need = frame_floats(rows, cols, n_oct, 9);
+    const size_t need = frame_floats(rows, cols, n_oct, 19);  // 5 G + 4 D + 5 float2 gradient maps
     if (need > h->ws_full_floats) {
         if (h->ws_full) cudaFree(h->ws_full);
         h->ws_full = nullptr; h->ws_full_floats = 0;
@@ -168,14 +175,16 @@ int run_pipeline(SiftB200* h, const float* d_imgs, const uint8_t* d_imgs8, int n
         if (timing) cudaEventRecord(h->ev[1], st);
         for (int o = 0; o < n_oct; ++o) h->launches += launch_octave(pv, o, nf, false, st);
         if (timing) cudaEventRecord(h->ev[2], st);
-        h->launches += launch_extrema(pv, h->db, nf, st);
+        h->launches += launch_gradient(pv, nf, st);
         if (timing) cudaEventRecord(h->ev[3], st);
-        h->launches += launch_orientation(pv, h->db, nf, st);
+        h->launches += launch_extrema(pv, h->db, nf, st);
         if (timing) cudaEventRecord(h->ev[4], st);
-        h->launches += launch_order_scan(h->db, nf, d_counts + f0, st);
+        h->launches += launch_orientation(pv, h->db, nf, st);
         if (timing) cudaEventRecord(h->ev[5], st);
+        h->launches += launch_order_scan(h->db, nf, d_counts + f0, st);
+        if (timing) cudaEventRecord(h->ev[6], st);
         h->launches += launch_describe(pv, h->db, nf, d_kp + (size_t)f0 * cap, d_desc + (size_t)f0 * cap * 128, cap, st);
-        if (timing) { cudaEventRecord(h->ev[6], st); h->ev_valid = true; }
+        if (timing) { cudaEventRecord(h->ev[7], st); h->ev_valid = true; }
     }
     CUDA_TRY(cudaGetLastError());
     return SIFT_B200_OK;
@@ -199,7 +208,7 @@ int sift_b200_create(SiftB200** out, int max_rows, int max_cols, int max_batch, 
     h->device = device; h->max_rows = max_rows; h->max_cols = max_cols; h->max_batch = max_batch; h->cap_kp = max_kp_per_frame;
     *out = h;
     CUDA_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-    h->ws_floats = frame_floats(max_rows, max_cols, 5, 7) * max_batch;
+    h->ws_floats = frame_floats(max_rows, max_cols, 5, 11) * max_batch;  // G0..G2, D0..D3, 2 x float2 gradient maps
     CUDA_TRY(cudaMalloc((void**)&h->ws, h->ws_floats * sizeof(float)));
     DetectBuf& db = h->db;
     db.cap_r = max_kp_per_frame;
@@ -507,6 +516,7 @@ int sift_b200_find_scale_space_extrema(SiftB200* h, const float* gpyr, const flo
     if ((rc = make_view(h->ws_full, rows, cols, n_octaves, 1, true, &pv))) return fail(rc, "make_view");
     if ((rc = copy_levels(pv, true, 5, const_cast<float*>(gpyr), true, h->stream))) return rc;
     if ((rc = copy_levels(pv, false, 4, const_cast<float*>(dogpyr), true, h->stream))) return rc;
+    h->launches += launch_gradient(pv, 1, h->stream);
     h->launches += launch_extrema(pv, h->db, 1, h->stream);
     h->launches += launch_orientation(pv, h->db, 1, h->stream);
     h->launches += launch_order_scan(h->db, 1, h->d_counts, h->stream);
@@ -537,6 +547,7 @@ int sift_b200_cal_descriptor(SiftB200* h, const float* gpyr, int rows, int cols,
     CUDA_TRY(cudaMalloc((void**)&d_err, 4));
     CUDA_TRY(cudaMemsetAsync(d_err, 0, 4, h->stream));
     CUDA_TRY(cudaMemcpyAsync(d_k, kps, (size_t)n * sizeof(SiftKeypoint), cudaMemcpyHostToDevice, h->stream));
+    h->launches += launch_gradient(pv, 1, h->stream);
     h->launches += launch_describe_given(pv, d_k, n, d_d, first_octave, d_err, h->stream);
     int err = 0;
     CUDA_TRY(cudaMemcpyAsync(desc, d_d, (size_t)n * 128 * 4, cudaMemcpyDeviceToHost, h->stream));
@@ -581,11 +592,11 @@ int sift_b200_set_stage_timing(SiftB200* h, int on) {
     return SIFT_B200_OK;
 }
 
-int sift_b200_get_stage_ms(SiftB200* h, float* ms7) {
-    if (!h || !ms7 || !h->ev_valid) return fail(SIFT_B200_ERR_ARG, "no stage timing recorded");
-    CUDA_TRY(cudaEventSynchronize(h->ev[6]));
-    for (int i = 0; i < 6; ++i) CUDA_TRY(cudaEventElapsedTime(&ms7[i], h->ev[i], h->ev[i + 1]));
-    CUDA_TRY(cudaEventElapsedTime(&ms7[6], h->ev[0], h->ev[6]));
+int sift_b200_get_stage_ms(SiftB200* h, float* ms8) {
+    if (!h || !ms8 || !h->ev_valid) return fail(SIFT_B200_ERR_ARG, "no stage timing recorded");
+    CUDA_TRY(cudaEventSynchronize(h->ev[7]));
+    for (int i = 0; i < 7; ++i) CUDA_TRY(cudaEventElapsedTime(&ms8[i], h->ev[i], h->ev[i + 1]));
+    CUDA_TRY(cudaEventElapsedTime(&ms8[7], h->ev[0], h->ev[7]));
     return SIFT_B200_OK;
 }
 

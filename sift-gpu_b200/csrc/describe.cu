@@ -10,10 +10,10 @@
 // keypoint, one pass:
 //   - the 4 cell-rows of the descriptor grid are split in two pairs p (a in {2p, 2p+1}); an 8-lane group owns (pair, window
 //     row): its lanes walk the row's j-interval 2p-1 <= rbin < 2p+2, -1 < cbin < 4 (two slab inequalities, widened by a
-//     pixel; the reference's exact test decides), two samples per lane per step so 8 independent gradient loads are in
-//     flight; lanes of a group read consecutive pixels (coalesced 32-byte segments);
-//   - each sample is evaluated in place (gradient, fastAtan2, magnitude, Gaussian weight -- in the reference's operation
-//     order) and its trilinear votes that fall into the pair's cells go straight into THREAD-PRIVATE histograms
+//     pixel; the reference's exact test decides), one sample per lane per step with the next step's load already in
+//     flight; lanes of a group read consecutive pixels (coalesced 64-byte segments);
+//   - each sample reads {Mag, Ori} of its pixel from the level's gradient map (detect.cu: gradient_kernel, the reference's
+//     own per-sample arithmetic done once per pixel), applies the Gaussian weight, and its trilinear votes that fall into the pair's cells go straight into THREAD-PRIVATE histograms
 //     [2 cell-rows][4 cells][9 bins] in shared memory (layout [bin][thread]: conflict-free plain read-modify-write).
 //     A sample is evaluated 1.2 times on average (twice only when its two cell-rows straddle the pairs);
 //   - tail: 128 threads = 128 output elements: sum the 64 private copies of the owning pair (rotated, conflict-free),
@@ -34,22 +34,6 @@ constexpr int DESC_SMEM_BYTES = (PRIV_FLOATS + 2 * PRIV_BINS + 8) * 4 + 2 * 2 * 
 
 __device__ __forceinline__ int cv_round(float v) { return __float2int_rn(v); }
 __device__ __forceinline__ int cv_floor(float v) { return __float2int_rd(v); }
-
-// hal::fastAtan2 (degrees).  Branch-free min/max form of the scalar polynomial in oracle/oracle_prims.h: the quotient is
-// min/(max + eps) in both octants, so one division serves both and the result is bit-identical.
-__device__ __forceinline__ float fast_atan2_deg(float y, float x) {
-    const float s = (float)(180.0 / 3.1415926535897932384626433832795);
-    const float p1 = 0.9997878412794807f * s, p3 = -0.3258083974640975f * s, p5 = 0.1555786518463281f * s, p7 = -0.04432655554792128f * s;
-    const float ax = fabsf(x), ay = fabsf(y);
-    const float mn = fminf(ax, ay), mx = fmaxf(ax, ay);
-    const float c = mn / (mx + (float)2.2204460492503131e-16);
-    const float c2 = c * c;
-    float a = (((p7 * c2 + p5) * c2 + p3) * c2 + p1) * c;
-    a = ax >= ay ? a : 90.f - a;
-    a = x < 0 ? 180.f - a : a;
-    a = y < 0 ? 360.f - a : a;
-    return a;
-}
 
 // sum over the CTA (4 warps); every thread gets the result.  `red` = 4 floats of shared scratch.
 __device__ __forceinline__ float block_sum(float v, float* red, int tid) {
@@ -81,7 +65,8 @@ __device__ __forceinline__ bool slab(float k, float inv_k, float off, float lo_v
 }
 
 // calcSIFTDescriptor, src/sift.cpp:579-722, for one keypoint by one CTA.  dst: 128 floats in global memory.
-__device__ void calc_descriptor(const float* __restrict__ img, int rows, int cols, int pitch, float ptx, float pty, float ori, float scl,
+// mo: the level's gradient map {Mag, Ori} (detect.cu gradient_kernel) -- the values the reference computes per sample (:623-633).
+__device__ void calc_descriptor(const float2* __restrict__ mo, int rows, int cols, int pitch, float ptx, float pty, float ori, float scl,
                                 float* __restrict__ smem, float* __restrict__ dst) {
     const int tid = threadIdx.x;
     const int px = cv_round(ptx), py = cv_round(pty);
@@ -119,48 +104,47 @@ __device__ void calc_descriptor(const float* __restrict__ img, int rows, int col
             s_jhi[pp * NB + it - pp * nrows] = ok ? min(jmax, (int)ceilf(hi) + 1) : 0;
         }
         __syncthreads();
-        // flattened walk: a group advances through its rows (slot, slot+8, ...) one 16-sample step per iteration, so the four
-        // groups of a warp never wait for each other at row boundaries
+        // flattened walk: a group advances through its rows (slot, slot+8, ...) one 8-sample step per iteration (one sample per
+        // lane), so the four groups of a warp never wait for each other at row boundaries; the NEXT step's gradient-map load is
+        // issued before the current step's arithmetic (software pipeline).
         int r = slot - DT / 16, jb = 1, jhi = 0;
-        const float* rowp = img;
+        const float2* rowp = mo;
         float isin = 0.f, icos = 0.f;
-        for (;;) {
+        // advance (r, jb, jhi, rowp, isin, icos) to the next step; false when the group has no more work in this band
+        auto advance = [&]() -> bool {
+            jb += 8;
             if (jb > jhi) {
                 do {
                     r += DT / 16;
-                    if (r >= nrows) break;
+                    if (r >= nrows) return false;
                     jb = s_jlo[p * NB + r];
                     jhi = s_jhi[p * NB + r];
                 } while (jb > jhi);
-                if (r >= nrows) break;
                 const int i = band0 + r;
-                rowp = img + (size_t)(py + i) * pitch + px;
+                rowp = mo + (size_t)(py + i) * pitch + px;
                 isin = i * sin_t;
                 icos = i * cos_t;
             }
-            const int j0 = jb + gl;
-            jb += 16;
-            float dxv[2], dyv[2];
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                const int j = min(j0 + 8 * u, jmax);  // clamped: always an interior pixel, loads are unconditional
-                const float* q = rowp + j;
-                dxv[u] = __ldg(q + 1) - __ldg(q - 1);
-                dyv[u] = __ldg(q - pitch) - __ldg(q + pitch);
-            }
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                const int j = j0 + 8 * u;
-                const float c_rot = j * cos_t - isin;
-                const float r_rot = j * sin_t + icos;
+            return true;
+        };
+        bool more = advance();
+        float2 cur = make_float2(0.f, 0.f);
+        if (more) cur = __ldg(rowp + min(jb + gl, jmax));  // clamped: always an interior pixel
+        while (more) {
+            const int j = jb + gl, jhi_c = jhi;
+            const float isin_c = isin, icos_c = icos;
+            more = advance();
+            float2 nxt = make_float2(0.f, 0.f);
+            if (more) nxt = __ldg(rowp + min(jb + gl, jmax));
+            {
+                const float c_rot = j * cos_t - isin_c;
+                const float r_rot = j * sin_t + icos_c;
                 float rbin = r_rot + DW / 2 - 0.5f;
                 float cbin = c_rot + DW / 2 - 0.5f;
-                const bool acc = j <= jhi && rbin > -1 && rbin < DW && cbin > -1 && cbin < DW;  // (:620)
-                const float o_ = fast_atan2_deg(dyv[u], dxv[u]);
-                const float m_ = sqrtf(dxv[u] * dxv[u] + dyv[u] * dyv[u]);
+                const bool acc = j <= jhi_c && rbin > -1 && rbin < DW && cbin > -1 && cbin < DW;  // (:620)
                 const float w_ = expf((c_rot * c_rot + r_rot * r_rot) * exp_scale);
-                float obin = (o_ - ori) * bins_per_rad;
-                const float mag = m_ * w_;
+                float obin = (cur.y - ori) * bins_per_rad;
+                const float mag = cur.x * w_;
                 const int r0 = cv_floor(rbin), c0 = cv_floor(cbin);
                 int o0 = cv_floor(obin);
                 rbin -= r0; cbin -= c0; obin -= o0;
@@ -184,6 +168,7 @@ __device__ void calc_descriptor(const float* __restrict__ img, int rows, int col
                     v1 = v_rc11 * obin; priv[i11 * DT] += v_rc11 - v1; priv[(i11 + 1) * DT] += v1;
                 }
             }
+            cur = nxt;
         }
         __syncthreads();
     }
@@ -236,7 +221,7 @@ __global__ void __launch_bounds__(DT, 6)
         const int octave = rec.octave & 255, layer = (rec.octave >> 8) & 255;
         const float scale = 1.f / (1 << octave);
         const OctaveView& ov = pv.oct[octave];
-        const float* img = ov.G[layer] + (size_t)f * ov.frame_stride;
+        const float2* img = ov.MO[layer] + (size_t)f * ov.frame_stride;
         const float size = rec.size * scale;
         for (int k = 0; k < np; ++k) {
             const int slot = base + k;
@@ -274,7 +259,7 @@ __global__ void __launch_bounds__(DT)
         float angle = 360.f - kp.angle;
         if (fabsf(angle - 360.f) < 1.1920928955078125e-7f) angle = 0.f;
         const float size = kp.size * scale;
-        calc_descriptor(ov.G[layer], ov.rows, ov.cols, ov.pitch, kp.x * scale, kp.y * scale, angle, size * 0.5f, smem, desc_out + (size_t)p * 128);
+        calc_descriptor(ov.MO[layer], ov.rows, ov.cols, ov.pitch, kp.x * scale, kp.y * scale, angle, size * 0.5f, smem, desc_out + (size_t)p * 128);
     }
 }
 

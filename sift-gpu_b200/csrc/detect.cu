@@ -11,6 +11,7 @@
 //                       (:493-511) becomes val >= max of three 3x3 maxima, with no divergent probing.  The rare
 //                       survivors run the Taylor refinement + contrast/edge rejection inline and append a 32-byte
 //                       record through one atomic counter per frame.
+//   gradient_kernel     {magnitude, fastAtan2 orientation} of every pixel of G1/G2, once, for the two window consumers.
 //   orientation_kernel  warp per refined point; lanes stride over the window and vote into LANE-PRIVATE 36-bin
 //                       histograms in shared memory ([bin][lane], conflict-free plain adds: shared float atomics
 //                       are CAS loops on sm_100a), summed with a rotated read; shuffle max-reduce, peak split.
@@ -206,6 +207,34 @@ __global__ void __launch_bounds__(128) refine_kernel(const __grid_constant__ Pyr
     }
 }
 
+// ---- gradient maps ------------------------------------------------------------------------------------------------
+// Both calcOrientationHist (:413-426) and calcSIFTDescriptor (:623-633) evaluate, per window sample,
+//   dx = I(y,x+1)-I(y,x-1), dy = I(y-1,x)-I(y+1,x), Mag = sqrt(dx*dx+dy*dy), Ori = fastAtan2(dy,dx)
+// on a Gaussian level.  Windows of neighbouring keypoints overlap and a frame has more window samples (~9 M) than level
+// pixels (2*sumP = 5.5 M), so the pair {Mag, Ori} is computed ONCE per pixel here -- same operations, bit-identical values --
+// and the two consumers gather one float2 per sample instead of four floats plus the atan2/sqrt arithmetic.
+// Thread per pixel, 32x8 tiles flattened over octaves; rows are read coalesced, x+-1 neighbours come from L1.
+__global__ void __launch_bounds__(256) gradient_kernel(const __grid_constant__ PyrView pv) {
+    int o = 0;
+#pragma unroll 1
+    for (int k = 1; k < pv.n_oct; ++k)
+        if ((int)blockIdx.x >= pv.oct[k].grad_tile_base) o = k;
+    const OctaveView& ov = pv.oct[o];
+    const int t = blockIdx.x - ov.grad_tile_base;
+    const int x = (t % ov.grad_tiles_x) * 32 + (threadIdx.x & 31);
+    const int y = (t / ov.grad_tiles_x) * 8 + (threadIdx.x >> 5);
+    if (x <= 0 || y <= 0 || x >= ov.cols - 1 || y >= ov.rows - 1) return;  // only 0 < y < rows-1, 0 < x < cols-1 is ever sampled
+    const size_t p = (size_t)blockIdx.y * ov.frame_stride + (size_t)y * ov.pitch + x;
+#pragma unroll
+    for (int l = 0; l < kNumScales; ++l) {
+        if (ov.MO[l] == nullptr) continue;
+        const float* q = ov.G[l] + p;
+        const float dx = __ldg(q + 1) - __ldg(q - 1);
+        const float dy = __ldg(q - ov.pitch) - __ldg(q + ov.pitch);
+        ov.MO[l][p] = make_float2(sqrtf(dx * dx + dy * dy), fast_atan2_deg(dy, dx));
+    }
+}
+
 // ---- orientation: calcOrientationHist + peak logic, src/sift.cpp:389-458, 518-541 ----------------------------
 constexpr int ORI_WARPS = 8;
 
@@ -223,7 +252,7 @@ __global__ void __launch_bounds__(ORI_WARPS * 32) orientation_kernel(const __gri
         const Refined rec = db.refined[(size_t)f * db.cap_r + i];
         const int o = rec.octave & 255, layer = (rec.octave >> 8) & 255;
         const OctaveView& ov = pv.oct[o];
-        const float* img = ov.G[layer] + (size_t)f * ov.frame_stride;
+        const float2* mo = ov.MO[layer] + (size_t)f * ov.frame_stride;  // {magnitude, orientation} of G[layer]
         const int rows = ov.rows, cols = ov.cols, pitch = ov.pitch;
         const int py = rec.rc >> 16, px = rec.rc & 0xffff;
         const float scl_octv = rec.size * 0.5f / (1 << o);
@@ -238,21 +267,21 @@ __global__ void __launch_bounds__(ORI_WARPS * 32) orientation_kernel(const __gri
         const int i_lo = max(-radius, 1 - py), i_hi = min(radius, rows - 2 - py);
         const int j_lo = max(-radius, 1 - px), j_hi = min(radius, cols - 2 - px);
         const int wj = j_hi - j_lo + 1;
-        if (wj > 0) {
+        if (wj > 0 && i_lo <= i_hi) {
             int ii = i_lo + lane / wj, jj = j_lo + lane % wj;  // flat raster index advanced by 32 without divisions
-            for (; ii <= i_hi; ) {
-                const float* q = img + (size_t)(py + ii) * pitch + (px + jj);
-                const float dx = __ldg(q + 1) - __ldg(q - 1);
-                const float dy = __ldg(q - pitch) - __ldg(q + pitch);
+            float2 cur = make_float2(0.f, 0.f);
+            if (ii <= i_hi) cur = __ldg(mo + (size_t)(py + ii) * pitch + (px + jj));
+            while (ii <= i_hi) {
+                int in = ii, jn = jj + 32;
+                while (jn > j_hi) { jn -= wj; ++in; }
+                float2 nxt = make_float2(0.f, 0.f);
+                if (in <= i_hi) nxt = __ldg(mo + (size_t)(py + in) * pitch + (px + jn));  // next sample's load overlaps this one's math
                 const float wgt = expf((ii * ii + jj * jj) * expf_scale);
-                const float ori = fast_atan2_deg(dy, dx);
-                const float mag = sqrtf(dx * dx + dy * dy);
-                int bin = cv_round((kOriBins / 360.f) * ori);
+                int bin = cv_round((kOriBins / 360.f) * cur.y);
                 if (bin >= kOriBins) bin -= kOriBins;
                 if (bin < 0) bin += kOriBins;
-                priv[bin * 32] += wgt * mag;
-                jj += 32;
-                while (jj > j_hi) { jj -= wj; ++ii; }
+                priv[bin * 32] += wgt * cur.x;
+                ii = in; jj = jn; cur = nxt;
             }
         }
         (void)w;
@@ -392,6 +421,11 @@ int launch_extrema(const PyrView& pv, const DetectBuf& db, int n_frames, cudaStr
     extrema_kernel<<<grid, EX_WARPS * 32, 0, st>>>(pv, db);
     refine_kernel<<<dim3(48, n_frames), 128, 0, st>>>(pv, db);
     return 2;
+}
+
+int launch_gradient(const PyrView& pv, int n_frames, cudaStream_t st) {
+    gradient_kernel<<<dim3(pv.total_grad_tiles, n_frames), 256, 0, st>>>(pv);
+    return 1;
 }
 
 int launch_orientation(const PyrView& pv, const DetectBuf& db, int n_frames, cudaStream_t st) {

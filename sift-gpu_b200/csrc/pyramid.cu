@@ -84,26 +84,44 @@ __device__ __forceinline__ void load_tile(float* __restrict__ sIn, const float* 
     }
 }
 
-// Masked tile load for the octave kernel: 16-byte loads.  The workspace pitch is a multiple of 32 floats and tx0 a multiple
-// of 32, so the window [tx0-20, tx0+52) is float4-aligned; the two extra columns on each side are dropped on the way in.
-__device__ __forceinline__ void load_tile_vec(float* __restrict__ sIn, const float* __restrict__ src, int rows, int cols, int pitch, int ty0, int tx0,
-                                              int tid) {
-    constexpr int HALO = kMaxRadius, IW = TW + 2 * HALO, IH = TH + 2 * HALO, IP = IW + 1;
-    constexpr int Q = (IW + 4) / 4;  // 18 float4 per row
-    for (int idx = tid; idx < IH * Q; idx += NT) {
-        const int y = idx / Q, q = idx - y * Q;
-        const int gy = ty0 - HALO + y, gx4 = tx0 - HALO - 2 + 4 * q;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (gy >= 0 && gy < rows - 1 && gx4 >= 0 && gx4 < pitch) v = __ldg(reinterpret_cast<const float4*>(src + (size_t)gy * pitch + gx4));
-        const float e[4] = {v.x, v.y, v.z, v.w};
-        float* out = sIn + y * IP + 4 * q - 2;
+// Masked tile load in two halves so that the global loads can be issued one tile ahead: tile_fetch (16-byte loads into
+// registers) and tile_stash (registers -> shared, applying the mask).  Needs a float4-aligned source: pitch % 4 == 0 and
+// tx0 % 32 == 0, so the window starts at tx0 - HALO - SLACK with SLACK = (-HALO) mod 4 extra columns dropped on the way in.
+// Mask = zero padding AND the reference's ">= rows-1 / cols-1 reads as zero" window fetch (src/sift.cpp:116).
+template <int HALO>
+struct TileIO {
+    static constexpr int SLACK = (4 - HALO % 4) % 4;
+    static constexpr int IW = TW + 2 * HALO, IH = TH + 2 * HALO, IP = IW + 1;
+    static constexpr int Q = (IW + 2 * SLACK) / 4;        // float4 per row
+    static constexpr int NSLOT = (IH * Q + NT - 1) / NT;  // float4 per thread
+
+    static __device__ __forceinline__ void fetch(float4 (&pre)[NSLOT], const float* __restrict__ src, int rows, int pitch, int ty0, int tx0, int tid) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int sx = 4 * q - 2 + k, gx = gx4 + k;
-            if (sx >= 0 && sx < IW) out[k] = (gx >= 0 && gx < cols - 1) ? e[k] : 0.f;
+        for (int k = 0; k < NSLOT; ++k) {
+            const int idx = tid + k * NT;
+            const int y = idx / Q, q = idx - y * Q;
+            const int gy = ty0 - HALO + y, gx4 = tx0 - HALO - SLACK + 4 * q;
+            pre[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (idx < IH * Q && gy >= 0 && gy < rows - 1 && gx4 >= 0 && gx4 < pitch) pre[k] = __ldg(reinterpret_cast<const float4*>(src + (size_t)gy * pitch + gx4));
         }
     }
-}
+    static __device__ __forceinline__ void stash(const float4 (&pre)[NSLOT], float* __restrict__ sIn, int cols, int tx0, int tid) {
+#pragma unroll
+        for (int k = 0; k < NSLOT; ++k) {
+            const int idx = tid + k * NT;
+            if (idx >= IH * Q) break;
+            const int y = idx / Q, q = idx - y * Q;
+            const int gx4 = tx0 - HALO - SLACK + 4 * q;
+            const float e[4] = {pre[k].x, pre[k].y, pre[k].z, pre[k].w};
+            float* out = sIn + y * IP + 4 * q - SLACK;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int sx = 4 * q - SLACK + c, gx = gx4 + c;
+                if (sx >= 0 && sx < IW) out[c] = (gx >= 0 && gx < cols - 1) ? e[c] : 0.f;
+            }
+        }
+    }
+};
 
 constexpr int H_OFF1 = 0;
 constexpr int H_OFF2 = H_OFF1 + (TH + 2 * 4) * HP;
@@ -124,16 +142,22 @@ struct OctArgs {
     size_t nframe_stride;
 };
 
+// One CTA per tile, 3 CTAs per SM.  (A persistent variant that kept the next tile's loads in flight in registers was
+// measured slower: 128 registers -> 2 CTAs/SM cost more than the exposed load latency it removed; profiles/README.md.)
 __global__ void __launch_bounds__(NT, 3) octave_kernel(const OctArgs a) {
     extern __shared__ float smem[];
     float* sIn = smem;
     float* sH = smem + OCT_IN;
+    using IO = TileIO<OCT_HALO>;
     const int tid = threadIdx.x;
     const int tx0 = blockIdx.x * TW, ty0 = blockIdx.y * TH;
-    const size_t foff = (size_t)blockIdx.z * a.frame_stride;
-    const float* G0 = a.G0 + foff;
-
-    load_tile_vec(sIn, G0, a.rows, a.cols, a.pitch, ty0, tx0, tid);
+    const int f = blockIdx.z;
+    const size_t foff = (size_t)f * a.frame_stride;
+    {
+        float4 pre[IO::NSLOT];
+        IO::fetch(pre, a.G0 + foff, a.rows, a.pitch, ty0, tx0, tid);
+        IO::stash(pre, sIn, a.cols, tx0, tid);
+    }
     __syncthreads();
     hpass<4, OCT_HALO>(sIn, sH + H_OFF4, tid);
     hpass<3, OCT_HALO>(sIn, sH + H_OFF3, tid);
@@ -149,8 +173,8 @@ __global__ void __launch_bounds__(NT, 3) octave_kernel(const OctArgs a) {
     fir8<4, HP>(sH + H_OFF4 + (rg * GRP) * HP + x, g4);
 
     const int gx = tx0 + x;
-    if (gx >= a.cols) return;
     constexpr int IP = TW + 2 * OCT_HALO + 1;
+    if (gx >= a.cols) return;
 #pragma unroll
     for (int k = 0; k < GRP; ++k) {
         const int gy = ty0 + rg * GRP + k;
@@ -168,7 +192,7 @@ __global__ void __launch_bounds__(NT, 3) octave_kernel(const OctArgs a) {
         a.D3[p] = g4[k] - g3[k];
         if (a.nextG0 && !((gy | gx) & 1)) {
             const int ny = gy >> 1, nx = gx >> 1;
-            if (ny < a.nrows && nx < a.ncols) a.nextG0[(size_t)blockIdx.z * a.nframe_stride + (size_t)ny * a.npitch + nx] = g2[k];
+            if (ny < a.nrows && nx < a.ncols) a.nextG0[(size_t)f * a.nframe_stride + (size_t)ny * a.npitch + nx] = g2[k];
         }
     }
 }
@@ -180,14 +204,21 @@ constexpr int BASE_SMEM_BYTES = (BASE_IN + (TH + 2 * 4) * HP) * 4;
 
 __global__ void __launch_bounds__(NT, 4)
     base_blur_kernel(const float* __restrict__ src, const uint8_t* __restrict__ src8, size_t src_frame_stride, int src_pitch, float* __restrict__ dst,
-                     size_t dst_frame_stride, int dst_pitch, int rows, int cols) {
+                     size_t dst_frame_stride, int dst_pitch, int rows, int cols, int vec) {
     extern __shared__ float smem[];
     float* sIn = smem;
     float* sH = smem + BASE_IN;
     const int tid = threadIdx.x;
     const int tx0 = blockIdx.x * TW, ty0 = blockIdx.y * TH;
-    load_tile<BASE_HALO>(sIn, src ? src + (size_t)blockIdx.z * src_frame_stride : nullptr, src8 ? src8 + (size_t)blockIdx.z * src_frame_stride : nullptr,
-                         rows, cols, src_pitch, ty0, tx0, tid);
+    if (vec) {  // float source, 16-byte aligned rows: float4 loads
+        using IO = TileIO<BASE_HALO>;
+        float4 pre[IO::NSLOT];
+        IO::fetch(pre, src + (size_t)blockIdx.z * src_frame_stride, rows, src_pitch, ty0, tx0, tid);
+        IO::stash(pre, sIn, cols, tx0, tid);
+    } else {
+        load_tile<BASE_HALO>(sIn, src ? src + (size_t)blockIdx.z * src_frame_stride : nullptr, src8 ? src8 + (size_t)blockIdx.z * src_frame_stride : nullptr,
+                             rows, cols, src_pitch, ty0, tx0, tid);
+    }
     __syncthreads();
     hpass<0, BASE_HALO>(sIn, sH, tid);
     __syncthreads();
@@ -265,8 +296,9 @@ void init_pyramid_kernels() {
 
 int launch_base_blur(const float* src, size_t src_frame_stride, int src_pitch, const uint8_t* src_u8, const OctaveView& o0, int n_frames, cudaStream_t st) {
     dim3 grid((o0.cols + TW - 1) / TW, (o0.rows + TH - 1) / TH, n_frames);
+    const int vec = !src_u8 && src_pitch % 4 == 0 && src_frame_stride % 4 == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0;
     base_blur_kernel<<<grid, NT, BASE_SMEM_BYTES, st>>>(src_u8 ? nullptr : src, src_u8, src_frame_stride, src_pitch, o0.G[0], o0.frame_stride, o0.pitch, o0.rows,
-                                                       o0.cols);
+                                                       o0.cols, vec);
     return 1;
 }
 

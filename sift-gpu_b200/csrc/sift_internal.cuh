@@ -3,7 +3,8 @@
 // Data layout in HBM (per handle, for up to max_batch frames F):
 //   per octave o: G[0..2] (G[3..4] only for the stage-level pyramid API) and D[0..3], each
 //   [F][rows_o][pitch_o] float32 with pitch_o = cols_o rounded up to 32 floats (128-byte rows so every
-//   warp-wide row segment is a whole number of 128-byte lines).
+//   warp-wide row segment is a whole number of 128-byte lines); MO[1..2] = {gradient magnitude, orientation}
+//   of G1/G2 as float2 with the same pitch (all five in the stage-level API).
 //   refined-point records, orientation peaks and ordering arrays: [F][cap_refined].
 #pragma once
 #include <cuda_runtime.h>
@@ -20,21 +21,26 @@ constexpr int kImgBorder = 5;      // src/sift.cpp:21
 constexpr int kMaxInterpSteps = 5; // src/sift.cpp:24
 constexpr int kOriBins = 36;       // src/sift.cpp:27
 constexpr int kMaxPeaks = 18;      // strict local maxima of a 36-bin circular histogram
+constexpr int kNumSMs = 148;      // B200
 constexpr int kMaxRadius = 18;     // floor(3*sig[4]) = floor(3*6.196774)
 
 struct OctaveView {
     float* G[kNumScales];     // Gaussian levels (G[3], G[4] may be null in the fused pipeline)
     float* D[kNumScales - 1]; // DoG levels
+    float2* MO[kNumScales];   // per-pixel gradient {magnitude, fastAtan2 orientation in degrees} of G[i] (null if not built)
     int rows, cols, pitch;    // pitch in floats
     size_t frame_stride;      // floats between consecutive frames of one level
     int tile_base;            // first extrema strip (30x16 outputs) of this octave in the flattened strip index
     int tiles_x;
+    int grad_tile_base;       // first 32x8 gradient tile of this octave in the flattened tile index
+    int grad_tiles_x;
 };
 
 struct PyrView {
     OctaveView oct[kMaxOctaves];
     int n_oct;
     int total_tiles;
+    int total_grad_tiles;
 };
 
 // One record per extremum that survived adjustLocalExtrema (src/sift.cpp:287-388).
@@ -76,6 +82,7 @@ int launch_octave(const PyrView& pv, int o, int n_frames, bool write_all_levels,
 int launch_generic_blur(const float* src, float* dst, int rows, int cols, const float* d_taps, int radius, int taps_hi, cudaStream_t st);
 int launch_dog(const PyrView& pv, int n_frames, cudaStream_t st);
 int launch_upsample2x(const float* src, float* dst, int rows, int cols, int n_frames, cudaStream_t st);
+int launch_gradient(const PyrView& pv, int n_frames, cudaStream_t st);
 int launch_extrema(const PyrView& pv, const DetectBuf& db, int n_frames, cudaStream_t st);
 int launch_orientation(const PyrView& pv, const DetectBuf& db, int n_frames, cudaStream_t st);
 int launch_order_scan(const DetectBuf& db, int n_frames, int* d_counts, cudaStream_t st);

@@ -102,11 +102,11 @@ void SIFT_NCL(InputArray image, std::vector<KeyPoint>& keypoints, OutputArray de
         const int rc = sift_b200_detect_describe(h, img.ptr<float>(0), img.rows, img.cols, (size_t)img.step1() * sizeof(float), kp.data(), desc.data(), cap, &n);
         if (rc == SIFT_B200_ERR_CAPACITY) { cap = n + n / 8 + 64; continue; }  // grow and redo: the reference has no cap
         if (rc != SIFT_B200_OK) raise("SIFT_NCL");
-        float ms[7];
+        float ms[8];
         if (sift_b200_get_stage_ms(h, ms) == SIFT_B200_OK) {  // the reference's three timer lines (src/sift.cpp:70,80,88)
             printf("pyramid construction time: %g\n", ms[0] + ms[1]);
-            printf("keypoint localization time: %g\n", ms[2] + ms[3] + ms[4]);
-            printf("descriptor extraction time: %g\n", ms[5]);
+            printf("keypoint localization time: %g\n", ms[2] + ms[3] + ms[4] + ms[5]);
+            printf("descriptor extraction time: %g\n", ms[6]);
         }
         keypoints.resize(n);
         if (n) std::memcpy((void*)keypoints.data(), kp.data(), sizeof(SiftKeypoint) * n);
