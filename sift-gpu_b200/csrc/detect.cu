@@ -213,25 +213,63 @@ __global__ void __launch_bounds__(128) refine_kernel(const __grid_constant__ Pyr
 // on a Gaussian level.  Windows of neighbouring keypoints overlap and a frame has more window samples (~9 M) than level
 // pixels (2*sumP = 5.5 M), so the pair {Mag, Ori} is computed ONCE per pixel here -- same operations, bit-identical values --
 // and the two consumers gather one float2 per sample instead of four floats plus the atan2/sqrt arithmetic.
-// Thread per pixel, 32x8 tiles flattened over octaves; rows are read coalesced, x+-1 neighbours come from L1.
-__global__ void __launch_bounds__(256) gradient_kernel(const __grid_constant__ PyrView pv) {
+// Warp = strip of 32 columns x GR_ROWS rows, 128-byte aligned (full-line loads and float2 stores).  All GR_ROWS+2 row loads of
+// a level are issued before any arithmetic (memory-level parallelism: the kernel is bandwidth/latency bound, not compute
+// bound); dx comes from two shuffles per row (the strip's left/right neighbours are fetched by lanes 0 and 31), dy from the
+// rows in registers.
+constexpr int GR_COLS = 32, GR_ROWS = 8, GR_WARPS = 4;
+
+template <int NL>
+__device__ __forceinline__ void gradient_strip(const float* const (&G)[NL], float2* const (&MO)[NL], int rows, int cols, int pitch, int x, int y0, int y1,
+                                               int lane) {
+    const bool col_out = x >= 1 && x < cols - 1;
+    const int xc = x < cols ? x : cols - 1;
+    // halo column fetched by this lane (lane 0: x-1, lane 31: x+1), clamped into the row; other lanes never use it
+    const int xh = lane == 0 ? max(x - 1, 0) : min(x + 1, cols - 1);
+    const bool has_h = lane == 0 || lane == 31;
+#pragma unroll
+    for (int l = 0; l < NL; ++l) {
+        float v[GR_ROWS + 2], h[GR_ROWS];
+#pragma unroll
+        for (int k = 0; k < GR_ROWS + 2; ++k) v[k] = __ldg(G[l] + (size_t)min(y0 - 1 + k, rows - 1) * pitch + xc);
+#pragma unroll
+        for (int k = 0; k < GR_ROWS; ++k) h[k] = has_h ? __ldg(G[l] + (size_t)min(y0 + k, rows - 1) * pitch + xh) : 0.f;
+#pragma unroll
+        for (int k = 0; k < GR_ROWS; ++k) {
+            float right = __shfl_down_sync(0xffffffffu, v[k + 1], 1), left = __shfl_up_sync(0xffffffffu, v[k + 1], 1);
+            if (lane == 0) left = h[k];
+            if (lane == 31) right = h[k];
+            const float dx = right - left;
+            const float dy = v[k] - v[k + 2];
+            if (col_out && y0 + k < y1) MO[l][(size_t)(y0 + k) * pitch + x] = make_float2(sqrtf(dx * dx + dy * dy), fast_atan2_deg(dy, dx));
+        }
+    }
+}
+
+// full = 0: levels 1,2 (the fused pipeline); full = 1: all five levels (stage-level API)
+__global__ void __launch_bounds__(GR_WARPS * 32, 8) gradient_kernel(const __grid_constant__ PyrView pv, int full) {
+    const int lane = threadIdx.x & 31;
+    const int strip = blockIdx.x * GR_WARPS + (threadIdx.x >> 5);
+    if (strip >= pv.total_grad_tiles) return;
     int o = 0;
 #pragma unroll 1
     for (int k = 1; k < pv.n_oct; ++k)
-        if ((int)blockIdx.x >= pv.oct[k].grad_tile_base) o = k;
+        if (strip >= pv.oct[k].grad_tile_base) o = k;
     const OctaveView& ov = pv.oct[o];
-    const int t = blockIdx.x - ov.grad_tile_base;
-    const int x = (t % ov.grad_tiles_x) * 32 + (threadIdx.x & 31);
-    const int y = (t / ov.grad_tiles_x) * 8 + (threadIdx.x >> 5);
-    if (x <= 0 || y <= 0 || x >= ov.cols - 1 || y >= ov.rows - 1) return;  // only 0 < y < rows-1, 0 < x < cols-1 is ever sampled
-    const size_t p = (size_t)blockIdx.y * ov.frame_stride + (size_t)y * ov.pitch + x;
-#pragma unroll
-    for (int l = 0; l < kNumScales; ++l) {
-        if (ov.MO[l] == nullptr) continue;
-        const float* q = ov.G[l] + p;
-        const float dx = __ldg(q + 1) - __ldg(q - 1);
-        const float dy = __ldg(q - ov.pitch) - __ldg(q + ov.pitch);
-        ov.MO[l][p] = make_float2(sqrtf(dx * dx + dy * dy), fast_atan2_deg(dy, dx));
+    const int t = strip - ov.grad_tile_base;
+    const int rows = ov.rows, cols = ov.cols, pitch = ov.pitch;
+    const int x = (t % ov.grad_tiles_x) * GR_COLS + lane;
+    const int y0 = 1 + (t / ov.grad_tiles_x) * GR_ROWS;                     // only 0 < y < rows-1, 0 < x < cols-1 is ever sampled
+    const int y1 = min(y0 + GR_ROWS, rows - 1);
+    const size_t foff = (size_t)blockIdx.y * ov.frame_stride;
+    if (!full) {
+        const float* const G[2] = {ov.G[1] + foff, ov.G[2] + foff};
+        float2* const MO[2] = {ov.MO[1] + foff, ov.MO[2] + foff};
+        gradient_strip<2>(G, MO, rows, cols, pitch, x, y0, y1, lane);
+    } else {
+        const float* const G[5] = {ov.G[0] + foff, ov.G[1] + foff, ov.G[2] + foff, ov.G[3] + foff, ov.G[4] + foff};
+        float2* const MO[5] = {ov.MO[0] + foff, ov.MO[1] + foff, ov.MO[2] + foff, ov.MO[3] + foff, ov.MO[4] + foff};
+        gradient_strip<5>(G, MO, rows, cols, pitch, x, y0, y1, lane);
     }
 }
 
@@ -424,7 +462,8 @@ int launch_extrema(const PyrView& pv, const DetectBuf& db, int n_frames, cudaStr
 }
 
 int launch_gradient(const PyrView& pv, int n_frames, cudaStream_t st) {
-    gradient_kernel<<<dim3(pv.total_grad_tiles, n_frames), 256, 0, st>>>(pv);
+    const int full = pv.oct[0].MO[0] != nullptr;
+    gradient_kernel<<<dim3((pv.total_grad_tiles + GR_WARPS - 1) / GR_WARPS, n_frames), GR_WARPS * 32, 0, st>>>(pv, full);
     return 1;
 }
 

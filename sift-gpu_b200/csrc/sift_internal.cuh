@@ -32,7 +32,7 @@ struct OctaveView {
     size_t frame_stride;      // floats between consecutive frames of one level
     int tile_base;            // first extrema strip (30x16 outputs) of this octave in the flattened strip index
     int tiles_x;
-    int grad_tile_base;       // first 32x8 gradient tile of this octave in the flattened tile index
+    int grad_tile_base;       // first gradient strip (32x8 outputs) of this octave in the flattened strip index
     int grad_tiles_x;
 };
 
