@@ -127,15 +127,24 @@ __device__ void calc_descriptor(const float2* __restrict__ mo, int rows, int col
             }
             return true;
         };
-        bool more = advance();
-        float2 cur = make_float2(0.f, 0.f);
-        if (more) cur = __ldg(rowp + min(jb + gl, jmax));  // clamped: always an interior pixel
-        while (more) {
-            const int j = jb + gl, jhi_c = jhi;
-            const float isin_c = isin, icos_c = icos;
-            more = advance();
-            float2 nxt = make_float2(0.f, 0.f);
-            if (more) nxt = __ldg(rowp + min(jb + gl, jmax));
+        // three steps in flight: the gradient-map load of step k+2 is issued before the arithmetic of step k
+        struct Step { int j, jhi; float isin, icos; float2 mo; bool ok; };
+        auto issue = [&](Step& st) {
+            st.ok = advance();
+            st.mo = make_float2(0.f, 0.f);
+            if (st.ok) {
+                st.j = jb + gl; st.jhi = jhi; st.isin = isin; st.icos = icos;
+                st.mo = __ldg(rowp + min(st.j, jmax));  // clamped: always an interior pixel
+            }
+        };
+        Step s0, s1, s2;
+        issue(s0); issue(s1); issue(s2);
+        while (s0.ok) {
+            const int j = s0.j, jhi_c = s0.jhi;
+            const float isin_c = s0.isin, icos_c = s0.icos;
+            const float2 cur = s0.mo;
+            s0 = s1; s1 = s2;
+            issue(s2);
             {
                 const float c_rot = j * cos_t - isin_c;
                 const float r_rot = j * sin_t + icos_c;
@@ -168,7 +177,6 @@ __device__ void calc_descriptor(const float2* __restrict__ mo, int rows, int col
                     v1 = v_rc11 * obin; priv[i11 * DT] += v_rc11 - v1; priv[(i11 + 1) * DT] += v1;
                 }
             }
-            cur = nxt;
         }
         __syncthreads();
     }
