@@ -386,8 +386,8 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--frames", type=int, default=128, help="frames per GPU per step")
-    ap.add_argument("--chunk", type=int, default=16, help="frames per internal pass (workspace size)")
+    ap.add_argument("--frames", type=int, default=256, help="frames per GPU per step")
+    ap.add_argument("--chunk", type=int, default=32, help="frames per internal pass (workspace size)")
     ap.add_argument("--cap", type=int, default=6144, help="keypoint capacity per frame")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])

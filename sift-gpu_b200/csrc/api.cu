@@ -6,6 +6,7 @@
 // CPU fallback anywhere: if CUDA is unavailable every entry point returns SIFT_B200_ERR_CUDA.
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -36,6 +37,13 @@ struct SiftB200 {
     float* ws_full = nullptr;   // stage-level API: 9 levels per octave, one frame (lazy)
     size_t ws_full_floats = 0;
     DetectBuf db{};
+    // second lane: own workspace, detection buffers and stream, so that consecutive chunks of a batch overlap
+    // (one chunk's latency-bound kernels fill the issue slots the other's leave idle).  Allocated on first use.
+    float* ws2 = nullptr;
+    DetectBuf db2{};
+    cudaStream_t stream2 = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join[2] = {};
+    int lanes = 2;
     float* d_img = nullptr;     // staging for host entry points [max_batch][max_rows*max_cols]
     SiftKeypoint* d_kp = nullptr;
     float* d_desc = nullptr;
@@ -156,36 +164,105 @@ int copy_levels(const PyrView& pv, bool gauss, int per, float* packed, bool to_d
     return SIFT_B200_OK;
 }
 
-int run_pipeline(SiftB200* h, const float* d_imgs, const uint8_t* d_imgs8, int n_frames, int rows, int cols, SiftKeypoint* d_kp, float* d_desc,
-                 int* d_counts, int cap, cudaStream_t st) {
+int alloc_detectbuf(DetectBuf& db, size_t F, int cap_r) {
+    db.cap_r = cap_r;
+    db.cap_r_pow2 = next_pow2(db.cap_r);
+    const size_t C = db.cap_r;
+    db.cap_c = 4 * db.cap_r < 16384 ? 16384 : 4 * db.cap_r;  // extrema before refinement (20-85 % survive, SURVEY 8(a8))
+    CUDA_TRY(cudaMalloc((void**)&db.cand, F * (size_t)db.cap_c * sizeof(uint32_t)));
+    CUDA_TRY(cudaMalloc((void**)&db.n_cand, F * sizeof(int)));
+    CUDA_TRY(cudaMalloc((void**)&db.refined, F * C * sizeof(Refined)));
+    CUDA_TRY(cudaMalloc((void**)&db.n_refined, F * sizeof(int)));
+    CUDA_TRY(cudaMalloc((void**)&db.angles, F * C * kMaxPeaks * sizeof(float)));
+    CUDA_TRY(cudaMalloc((void**)&db.n_peaks, F * C * sizeof(int)));
+    CUDA_TRY(cudaMalloc((void**)&db.order, F * C * sizeof(int)));
+    CUDA_TRY(cudaMalloc((void**)&db.kp_offset, F * C * sizeof(int)));
+    CUDA_TRY(cudaMalloc((void**)&db.sort_tmp, F * (size_t)db.cap_r_pow2 * sizeof(unsigned long long)));
+    return SIFT_B200_OK;
+}
+
+void free_detectbuf(DetectBuf& db) {
+    cudaFree(db.cand); cudaFree(db.n_cand); cudaFree(db.refined); cudaFree(db.n_refined); cudaFree(db.angles); cudaFree(db.n_peaks);
+    cudaFree(db.order); cudaFree(db.kp_offset); cudaFree(db.sort_tmp);
+    db = DetectBuf{};
+}
+
+int ensure_lane2(SiftB200* h) {
+    if (h->ws2) return SIFT_B200_OK;
+    CUDA_TRY(cudaMalloc((void**)&h->ws2, h->ws_floats * sizeof(float)));
+    int rc = alloc_detectbuf(h->db2, h->max_batch, h->cap_kp);
+    if (rc) return rc;
+    CUDA_TRY(cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    for (auto& e : h->ev_join) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    return SIFT_B200_OK;
+}
+
+// The whole path for ONE chunk (nf <= max_batch frames) on stream st, in lane `lane`'s workspace: 12 launches.
+int enqueue_chunk(SiftB200* h, int lane, const float* d_imgs, const uint8_t* d_imgs8, int nf, int rows, int cols, SiftKeypoint* d_kp, float* d_desc,
+                  int* d_counts, int cap, cudaStream_t st, bool timing) {
+    const int n_oct = 5;  // SIFT_NCL hard-codes 5 octaves (src/sift.cpp:67-68,78)
+    PyrView pv;
+    const int rc = make_view(lane ? h->ws2 : h->ws, rows, cols, n_oct, nf, false, &pv);
+    if (rc) return fail(rc, "make_view");
+    const DetectBuf& db = lane ? h->db2 : h->db;
+    const size_t fs = (size_t)rows * cols;
+    if (timing) cudaEventRecord(h->ev[0], st);
+    h->launches += launch_base_blur(d_imgs, fs, cols, d_imgs8, pv.oct[0], nf, st);
+    if (timing) cudaEventRecord(h->ev[1], st);
+    for (int o = 0; o < n_oct; ++o) h->launches += launch_octave(pv, o, nf, false, st);
+    if (timing) cudaEventRecord(h->ev[2], st);
+    h->launches += launch_gradient(pv, nf, st);
+    if (timing) cudaEventRecord(h->ev[3], st);
+    h->launches += launch_extrema(pv, db, nf, st);
+    if (timing) cudaEventRecord(h->ev[4], st);
+    h->launches += launch_orientation(pv, db, nf, st);
+    if (timing) cudaEventRecord(h->ev[5], st);
+    h->launches += launch_order_scan(db, nf, d_counts, st);
+    if (timing) cudaEventRecord(h->ev[6], st);
+    h->launches += launch_describe(pv, db, nf, d_kp, d_desc, cap, st);
+    if (timing) { cudaEventRecord(h->ev[7], st); h->ev_valid = true; }
+    return SIFT_B200_OK;
+}
+
+int check_run(SiftB200* h, int n_frames, int rows, int cols, int cap) {
     int rc = check_dims(h, rows, cols);
     if (rc) return rc;
     if (n_frames < 0 || cap < 1 || cap > h->cap_kp) return fail(SIFT_B200_ERR_ARG, "cap must be in [1, max_kp_per_frame]");
     if ((rows >> 4) < 1 || (cols >> 4) < 1) return fail(SIFT_B200_ERR_TOO_SMALL, "image smaller than 16 px: octave 4 would be empty (reference throws in cv::resize)");
     CUDA_TRY(cudaSetDevice(h->device));
-    const int n_oct = 5;  // SIFT_NCL hard-codes 5 octaves (src/sift.cpp:67-68,78)
-    for (int f0 = 0; f0 < n_frames; f0 += h->max_batch) {
+    return SIFT_B200_OK;
+}
+
+// n_frames in chunks of max_batch, asynchronous with respect to the host, ordered after / before the caller's stream st.
+// With two or more chunks the chunks alternate between two lanes (own workspace + stream, forked from and joined back to st).
+int run_pipeline(SiftB200* h, const float* d_imgs, const uint8_t* d_imgs8, int n_frames, int rows, int cols, SiftKeypoint* d_kp, float* d_desc,
+                 int* d_counts, int cap, cudaStream_t st) {
+    int rc = check_run(h, n_frames, rows, cols, cap);
+    if (rc) return rc;
+    const size_t fs = (size_t)rows * cols;
+    const int n_chunks = (n_frames + h->max_batch - 1) / h->max_batch;
+    const bool two = n_chunks >= 2 && h->lanes >= 2 && !h->stage_timing;
+    if (two) {
+        if ((rc = ensure_lane2(h))) return rc;
+        CUDA_TRY(cudaEventRecord(h->ev_fork, st));
+        CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_fork, 0));
+        CUDA_TRY(cudaStreamWaitEvent(h->stream2, h->ev_fork, 0));
+    }
+    for (int k = 0; k < n_chunks; ++k) {
+        const int f0 = k * h->max_batch;
         const int nf = n_frames - f0 < h->max_batch ? n_frames - f0 : h->max_batch;
-        PyrView pv;
-        rc = make_view(h->ws, rows, cols, n_oct, nf, false, &pv);
-        if (rc) return fail(rc, "make_view");
-        const bool timing = h->stage_timing && f0 + nf >= n_frames;
-        if (timing) cudaEventRecord(h->ev[0], st);
-        const size_t fs = (size_t)rows * cols;
-        h->launches += launch_base_blur(d_imgs ? d_imgs + f0 * fs : nullptr, fs, cols, d_imgs8 ? d_imgs8 + f0 * fs : nullptr, pv.oct[0], nf, st);
-        if (timing) cudaEventRecord(h->ev[1], st);
-        for (int o = 0; o < n_oct; ++o) h->launches += launch_octave(pv, o, nf, false, st);
-        if (timing) cudaEventRecord(h->ev[2], st);
-        h->launches += launch_gradient(pv, nf, st);
-        if (timing) cudaEventRecord(h->ev[3], st);
-        h->launches += launch_extrema(pv, h->db, nf, st);
-        if (timing) cudaEventRecord(h->ev[4], st);
-        h->launches += launch_orientation(pv, h->db, nf, st);
-        if (timing) cudaEventRecord(h->ev[5], st);
-        h->launches += launch_order_scan(h->db, nf, d_counts + f0, st);
-        if (timing) cudaEventRecord(h->ev[6], st);
-        h->launches += launch_describe(pv, h->db, nf, d_kp + (size_t)f0 * cap, d_desc + (size_t)f0 * cap * 128, cap, st);
-        if (timing) { cudaEventRecord(h->ev[7], st); h->ev_valid = true; }
+        const int lane = two ? (k & 1) : 0;
+        cudaStream_t cs = two ? (lane ? h->stream2 : h->stream) : st;
+        rc = enqueue_chunk(h, lane, d_imgs ? d_imgs + f0 * fs : nullptr, d_imgs8 ? d_imgs8 + f0 * fs : nullptr, nf, rows, cols, d_kp + (size_t)f0 * cap,
+                           d_desc + (size_t)f0 * cap * 128, d_counts + f0, cap, cs, h->stage_timing && k == n_chunks - 1);
+        if (rc) return rc;
+    }
+    if (two) {
+        CUDA_TRY(cudaEventRecord(h->ev_join[0], h->stream));
+        CUDA_TRY(cudaEventRecord(h->ev_join[1], h->stream2));
+        CUDA_TRY(cudaStreamWaitEvent(st, h->ev_join[0], 0));
+        CUDA_TRY(cudaStreamWaitEvent(st, h->ev_join[1], 0));
     }
     CUDA_TRY(cudaGetLastError());
     return SIFT_B200_OK;
@@ -211,20 +288,9 @@ int sift_b200_create(SiftB200** out, int max_rows, int max_cols, int max_batch, 
     CUDA_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     h->ws_floats = frame_floats(max_rows, max_cols, 5, 11) * max_batch;  // G0..G2, D0..D3, 2 x float2 gradient maps
     CUDA_TRY(cudaMalloc((void**)&h->ws, h->ws_floats * sizeof(float)));
-    DetectBuf& db = h->db;
-    db.cap_r = max_kp_per_frame;
-    db.cap_r_pow2 = next_pow2(db.cap_r);
-    const size_t F = max_batch, C = db.cap_r;
-    db.cap_c = 4 * db.cap_r < 16384 ? 16384 : 4 * db.cap_r;  // extrema before refinement (20-85 % survive, SURVEY 8(a8))
-    CUDA_TRY(cudaMalloc((void**)&db.cand, F * (size_t)db.cap_c * sizeof(uint32_t)));
-    CUDA_TRY(cudaMalloc((void**)&db.n_cand, F * sizeof(int)));
-    CUDA_TRY(cudaMalloc((void**)&db.refined, F * C * sizeof(Refined)));
-    CUDA_TRY(cudaMalloc((void**)&db.n_refined, F * sizeof(int)));
-    CUDA_TRY(cudaMalloc((void**)&db.angles, F * C * kMaxPeaks * sizeof(float)));
-    CUDA_TRY(cudaMalloc((void**)&db.n_peaks, F * C * sizeof(int)));
-    CUDA_TRY(cudaMalloc((void**)&db.order, F * C * sizeof(int)));
-    CUDA_TRY(cudaMalloc((void**)&db.kp_offset, F * C * sizeof(int)));
-    CUDA_TRY(cudaMalloc((void**)&db.sort_tmp, F * (size_t)db.cap_r_pow2 * sizeof(unsigned long long)));
+    const size_t F = max_batch;
+    if (int rc_db = alloc_detectbuf(h->db, F, max_kp_per_frame)) return rc_db;
+    if (const char* e = getenv("SIFT_B200_LANES")) h->lanes = atoi(e);
     CUDA_TRY(cudaMalloc((void**)&h->d_counts, F * sizeof(int)));
     CUDA_TRY(cudaMallocHost((void**)&h->h_counts, F * sizeof(int)));
     for (auto& e : h->ev) CUDA_TRY(cudaEventCreate(&e));
@@ -246,10 +312,12 @@ int sift_b200_destroy(SiftB200* h) {
     if (!h) return SIFT_B200_OK;
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
-    cudaFree(h->ws); cudaFree(h->ws_full);
-    cudaFree(h->db.cand); cudaFree(h->db.n_cand);
-    cudaFree(h->db.refined); cudaFree(h->db.n_refined); cudaFree(h->db.angles); cudaFree(h->db.n_peaks);
-    cudaFree(h->db.order); cudaFree(h->db.kp_offset); cudaFree(h->db.sort_tmp);
+    cudaFree(h->ws); cudaFree(h->ws_full); cudaFree(h->ws2);
+    free_detectbuf(h->db);
+    free_detectbuf(h->db2);
+    if (h->stream2) cudaStreamDestroy(h->stream2);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    for (auto& e : h->ev_join) if (e) cudaEventDestroy(e);
     cudaFree(h->d_img); cudaFree(h->d_kp); cudaFree(h->d_desc); cudaFree(h->d_counts);
     cudaFreeHost(h->h_counts);
     cudaFree(h->d_img2); cudaFree(h->d_kp2); cudaFree(h->d_desc2); cudaFree(h->d_counts2);
@@ -314,6 +382,10 @@ int sift_b200_detect_describe_batch_host(SiftB200* h, const float* imgs, int n_f
     CUDA_TRY(cudaSetDevice(h->device));
     if ((rc = ensure_staging(h))) return rc;
     if ((rc = ensure_pipeline(h))) return rc;
+    if ((rc = check_run(h, n_frames, rows, cols, cap))) return rc;
+    const bool two = h->lanes >= 2 && !h->stage_timing;
+    if (two && (rc = ensure_lane2(h))) return rc;
+    cudaStream_t cst[2] = {h->stream, two ? h->stream2 : h->stream};  // chunk k computes in lane k&1
     const size_t fs = (size_t)rows * cols;
     float* d_img[2] = {h->d_img, h->d_img2};
     SiftKeypoint* d_kp[2] = {h->d_kp, h->d_kp2};
@@ -345,11 +417,11 @@ int sift_b200_detect_describe_batch_host(SiftB200* h, const float* imgs, int n_f
         if (k >= 2) CUDA_TRY(cudaStreamWaitEvent(h->s_in, h->ev_comp[b], 0));   // chunk k-2 has consumed this input buffer
         CUDA_TRY(cudaMemcpyAsync(d_img[b], imgs + f0 * fs, nf * fs * sizeof(float), cudaMemcpyHostToDevice, h->s_in));
         CUDA_TRY(cudaEventRecord(h->ev_in[b], h->s_in));
-        CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_in[b], 0));
-        if (k >= 2) CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_out[b], 0)); // chunk k-2's results have left this output buffer
-        rc = run_pipeline(h, d_img[b], nullptr, nf, rows, cols, d_kp[b], d_desc[b], d_cnt[b], cap, h->stream);
+        CUDA_TRY(cudaStreamWaitEvent(cst[b], h->ev_in[b], 0));
+        if (k >= 2) CUDA_TRY(cudaStreamWaitEvent(cst[b], h->ev_out[b], 0)); // chunk k-2's results have left this output buffer
+        rc = enqueue_chunk(h, two ? b : 0, d_img[b], nullptr, nf, rows, cols, d_kp[b], d_desc[b], d_cnt[b], cap, cst[b], false);
         if (rc) return rc;
-        CUDA_TRY(cudaEventRecord(h->ev_comp[b], h->stream));
+        CUDA_TRY(cudaEventRecord(h->ev_comp[b], cst[b]));
         // results of chunk k-1 go out on s_out WHILE chunk k computes (queued before the wait on chunk k below)
         if (k >= 1 && (rc = flush(k - 1))) return rc;
         CUDA_TRY(cudaStreamWaitEvent(h->s_out, h->ev_comp[b], 0));
@@ -359,6 +431,7 @@ int sift_b200_detect_describe_batch_host(SiftB200* h, const float* imgs, int n_f
     if (n_chunks > 0 && (rc = flush(n_chunks - 1))) return rc;
     CUDA_TRY(cudaStreamSynchronize(h->s_out));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
+    if (two) CUDA_TRY(cudaStreamSynchronize(h->stream2));
     if (status) g_err = "keypoint capacity exceeded: outputs truncated";
     return status;
 }
