@@ -9,8 +9,8 @@
 // neighbouring samples hit the same bins.  This kernel is atomics-free and deterministic, one CTA (128 threads) per
 // keypoint, one pass:
 //   - the 4 cell-rows of the descriptor grid are split in two pairs p (a in {2p, 2p+1}); an 8-lane group owns (pair, window
-//     row): its lanes walk the row's j-interval 2p-1 <= rbin < 2p+2, -1 < cbin < 4 (two slab inequalities, widened by a
-//     pixel; the reference's exact test decides), one sample per lane per step with the next step's load already in
+//     row): its lanes walk the row's j-interval 2p-1 <= rbin < 2p+2, -1 < cbin < 4 (two slab inequalities rounded
+//     outwards; the reference's exact test decides), one sample per lane per step with the next step's load already in
 //     flight; lanes of a group read consecutive pixels (coalesced 64-byte segments);
 //   - each sample reads {Mag, Ori} of its pixel from the level's gradient map (detect.cu: gradient_kernel, the reference's
 //     own per-sample arithmetic done once per pixel), applies the Gaussian weight, and its trilinear votes that fall into the pair's cells go straight into THREAD-PRIVATE histograms
@@ -89,8 +89,8 @@ __device__ void calc_descriptor(const float2* __restrict__ mo, int rows, int col
     const int imin = max(-radius, 1 - py), imax = min(radius, rows - 2 - py);   // 0 < r < rows-1
 
     for (int k = tid * 4; k < PRIV_FLOATS; k += DT * 4) *reinterpret_cast<float4*>(s_priv + k) = make_float4(0.f, 0.f, 0.f, 0.f);
-    const int gl = tid & 7, grp = tid >> 3;
-    const int p = grp & 1, slot = grp >> 1;  // cell-row pair, row slot (8 slots per pair)
+    const int gl = tid & 7;
+    const int p = tid >> 6, slot = (tid >> 3) & 7;  // cell-row pair (its 64 threads are contiguous), row slot (8 slots per pair)
     float* priv = s_priv + tid;
     for (int band0 = imin; band0 <= imax; band0 += NB) {
         const int nrows = min(NB, imax - band0 + 1);
@@ -100,8 +100,10 @@ __device__ void calc_descriptor(const float2* __restrict__ mo, int rows, int col
             float lo = (float)jmin, hi = (float)jmax;
             bool ok = slab(sin_t, inv_s, i * cos_t + 1.5f, 2 * pp - 1.f, 2 * pp + 2.f, lo, hi);
             ok = ok && slab(cos_t, inv_c, -(i * sin_t) + 1.5f, -1.f, 4.f, lo, hi);
-            s_jlo[pp * NB + it - pp * nrows] = ok ? max(jmin, (int)floorf(lo) - 1) : 1;
-            s_jhi[pp * NB + it - pp * nrows] = ok ? min(jmax, (int)ceilf(hi) + 1) : 0;
+            // floor/ceil of the real-valued slab bounds already cover every sample the float test can accept (the bounds are
+            // accurate to ~1e-5 px; a sample that close to the boundary carries a ~1e-6 share of its vote)
+            s_jlo[pp * NB + it - pp * nrows] = ok ? max(jmin, (int)floorf(lo)) : 1;
+            s_jhi[pp * NB + it - pp * nrows] = ok ? min(jmax, (int)ceilf(hi)) : 0;
         }
         __syncthreads();
         // flattened walk: a group advances through its rows (slot, slot+8, ...) one 8-sample step per iteration (one sample per
@@ -184,13 +186,10 @@ __device__ void calc_descriptor(const float2* __restrict__ mo, int rows, int col
     // ---- tail, stage A: the 2 x 72 column sums over the 64 private copies of each pair (rotated read: conflict-free) ----
     for (int sidx = tid; sidx < 2 * PRIV_BINS; sidx += DT) {
         const int sp = sidx >= PRIV_BINS, bin = sidx - sp * PRIV_BINS;
-        const float* col = s_priv + bin * DT + sp * 8;
+        const float* col = s_priv + bin * DT + sp * (DT / 2);  // the 64 private copies of pair sp are contiguous
         float acc = 0.f;
-#pragma unroll 8
-        for (int g = 0; g < DT / 2; ++g) {
-            const int q = (g + tid) & (DT / 2 - 1);
-            acc += col[(q >> 3) * 16 + (q & 7)];  // q-th thread of pair sp: grp = 2*(q>>3)+sp, lane q&7
-        }
+#pragma unroll 16
+        for (int g = 0; g < DT / 2; ++g) acc += col[(g + tid) & (DT / 2 - 1)];
         s_sum[sidx] = acc;
     }
     __syncthreads();
