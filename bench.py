@@ -341,6 +341,21 @@ def run_ours(args, out):
     e2e = {"value": frames_total / t_host, "unit": "frames/s", "h2d_bytes_per_step": int(B * ROWS * COLS * 4),
            "d2h_bytes_per_step": int(hc.sum()) * 540 + 4 * B,
            "api": "sift_b200_detect_describe_batch_host (pinned host float32 frames in; host keypoints, descriptors, counts out)"}
+    # ---- extra: the same call with uint8 gray host frames (what src/main.cpp:84 holds before convertTo): 1/4 of the H2D bytes ----
+    host_u8 = torch.from_numpy(np.clip(np.rint(host_frames.numpy()), 0, 255).astype(np.uint8)).pin_memory()
+    step_host_u8 = lambda: s.detect_describe_batch_host_u8_ptr(host_u8.data_ptr(), B, ROWS, COLS, h_kp.data_ptr(), h_desc.data_ptr(), h_cnt.data_ptr(), cap)
+    step_host_u8()
+    barrier()
+    w0 = time.time()
+    t0 = time.perf_counter()
+    for _ in range(e_steps):
+        step_host_u8()
+    torch.cuda.synchronize(dev)
+    t_u8 = max_over_ranks((time.perf_counter() - t0) / e_steps, dev)
+    windows.append((w0, time.time()))
+    e2e_u8 = {"value": frames_total / t_u8, "unit": "frames/s", "h2d_bytes_per_step": int(B * ROWS * COLS),
+              "d2h_bytes_per_step": int(h_cnt.numpy().sum()) * 540 + 4 * B,
+              "api": "sift_b200_detect_describe_batch_host_u8 (frames rounded to uint8: a different input than the float frames above)"}
     clocks = sampler.stop(windows) if sampler else None
 
     cpu_base = None
@@ -352,7 +367,7 @@ def run_ours(args, out):
                 "config": {"workload": WORKLOAD, "frames_per_step_per_gpu": B, "chunk_frames": chunk, "keypoint_capacity": cap,
                            "mean_keypoints_per_frame": round(n_kp, 1), "parallelism": f"frame-sharded x{world}, no collectives",
                            "l2": f"inputs larger than L2: {B} frames x 8.3 MB per step, workspace {chunk} x 77 MB"},
-                "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "roofline_by_kernel": by_kernel,
+                "e2e": e2e, "e2e_u8": e2e_u8, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "roofline_by_kernel": by_kernel,
                 "roofline_pipeline": roofline_pipeline, "cpu_baseline": cpu_base}
         out.emit(json.dumps(line))
     s.close()

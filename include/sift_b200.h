@@ -80,6 +80,10 @@ int sift_b200_detect_describe_batch_dev(SiftB200* h, const float* d_imgs, int n_
 int sift_b200_detect_describe_batch_host(SiftB200* h, const float* imgs, int n_frames, int rows, int cols,
                                          SiftKeypoint* kp_out, float* desc_out, int* counts_out, int cap);
 
+/* Same with uint8 gray frames on the host (what src/main.cpp:84 holds before convertTo): a quarter of the PCIe traffic. */
+int sift_b200_detect_describe_batch_host_u8(SiftB200* h, const uint8_t* imgs, int n_frames, int rows, int cols,
+                                            SiftKeypoint* kp_out, float* desc_out, int* counts_out, int cap);
+
 /* u8 front end (src/main.cpp:84-85 semantics: gray u8 -> float32 without scaling), fused into the base
  * blur; device frames, otherwise identical to the batch_dev call. */
 int sift_b200_detect_describe_batch_dev_u8(SiftB200* h, const uint8_t* d_imgs, int n_frames, int rows, int cols,

@@ -374,8 +374,9 @@ static int ensure_pipeline(SiftB200* h) {
 // Host batch, software-pipelined over chunks of max_batch frames: H2D of chunk k+1 (stream s_in) and the exact-size
 // D2H of chunk k-1 (stream s_out) overlap the kernels of chunk k (h->stream).  The host only ever waits for the tiny
 // counts copy of the PREVIOUS chunk, after the next chunk's work has been queued, so the GPU never idles on the host.
-int sift_b200_detect_describe_batch_host(SiftB200* h, const float* imgs, int n_frames, int rows, int cols, SiftKeypoint* kp_out, float* desc_out,
-                                         int* counts_out, int cap) {
+static int batch_host_impl(SiftB200* h, const void* imgs_v, int elem, int n_frames, int rows, int cols, SiftKeypoint* kp_out, float* desc_out,
+                           int* counts_out, int cap) {
+    const unsigned char* imgs = static_cast<const unsigned char*>(imgs_v);  // elem = 4 (float32 frames) or 1 (uint8 frames)
     int rc = check_dims(h, rows, cols);
     if (rc) return rc;
     if (!imgs || !kp_out || !desc_out || !counts_out) return fail(SIFT_B200_ERR_ARG, "null buffer");
@@ -415,11 +416,12 @@ int sift_b200_detect_describe_batch_host(SiftB200* h, const float* imgs, int n_f
         const int b = k & 1, f0 = k * h->max_batch;
         const int nf = n_frames - f0 < h->max_batch ? n_frames - f0 : h->max_batch;
         if (k >= 2) CUDA_TRY(cudaStreamWaitEvent(h->s_in, h->ev_comp[b], 0));   // chunk k-2 has consumed this input buffer
-        CUDA_TRY(cudaMemcpyAsync(d_img[b], imgs + f0 * fs, nf * fs * sizeof(float), cudaMemcpyHostToDevice, h->s_in));
+        CUDA_TRY(cudaMemcpyAsync(d_img[b], imgs + (size_t)f0 * fs * elem, nf * fs * elem, cudaMemcpyHostToDevice, h->s_in));
         CUDA_TRY(cudaEventRecord(h->ev_in[b], h->s_in));
         CUDA_TRY(cudaStreamWaitEvent(cst[b], h->ev_in[b], 0));
         if (k >= 2) CUDA_TRY(cudaStreamWaitEvent(cst[b], h->ev_out[b], 0)); // chunk k-2's results have left this output buffer
-        rc = enqueue_chunk(h, two ? b : 0, d_img[b], nullptr, nf, rows, cols, d_kp[b], d_desc[b], d_cnt[b], cap, cst[b], false);
+        rc = enqueue_chunk(h, two ? b : 0, elem == 4 ? d_img[b] : nullptr, elem == 1 ? reinterpret_cast<const uint8_t*>(d_img[b]) : nullptr, nf, rows, cols,
+                           d_kp[b], d_desc[b], d_cnt[b], cap, cst[b], false);
         if (rc) return rc;
         CUDA_TRY(cudaEventRecord(h->ev_comp[b], cst[b]));
         // results of chunk k-1 go out on s_out WHILE chunk k computes (queued before the wait on chunk k below)
@@ -434,6 +436,16 @@ int sift_b200_detect_describe_batch_host(SiftB200* h, const float* imgs, int n_f
     if (two) CUDA_TRY(cudaStreamSynchronize(h->stream2));
     if (status) g_err = "keypoint capacity exceeded: outputs truncated";
     return status;
+}
+
+int sift_b200_detect_describe_batch_host(SiftB200* h, const float* imgs, int n_frames, int rows, int cols, SiftKeypoint* kp_out, float* desc_out,
+                                         int* counts_out, int cap) {
+    return batch_host_impl(h, imgs, 4, n_frames, rows, cols, kp_out, desc_out, counts_out, cap);
+}
+
+int sift_b200_detect_describe_batch_host_u8(SiftB200* h, const uint8_t* imgs, int n_frames, int rows, int cols, SiftKeypoint* kp_out, float* desc_out,
+                                            int* counts_out, int cap) {
+    return batch_host_impl(h, imgs, 1, n_frames, rows, cols, kp_out, desc_out, counts_out, cap);
 }
 
 int sift_b200_detect_describe(SiftB200* h, const float* img, int rows, int cols, size_t row_stride_bytes, SiftKeypoint* kp_out, float* desc_out, int cap,

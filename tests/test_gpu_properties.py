@@ -80,6 +80,12 @@ def test_batch_dev_equals_single_frames(pkg, synth):
     torch.cuda.synchronize()
     kpf, descf = s.detect_describe(u8[0].astype(np.float32))
     assert int(d_cnt8[0]) == len(kpf) and np.array_equal(d_desc8[0, : len(kpf)].cpu().numpy(), descf)
+    # ... and the uint8 host-batch entry point
+    import ctypes as C
+    h_cnt8 = np.zeros(5, dtype=np.int32)
+    rc = pkg.lib().sift_b200_detect_describe_batch_host_u8(s._h, u8.ctypes.data_as(C.c_void_p), 5, 360, 640, h_kp.ctypes.data_as(C.c_void_p),
+                                                           h_desc.ctypes.data_as(C.c_void_p), h_cnt8.ctypes.data_as(C.c_void_p), cap)
+    assert rc == pkg.OK and np.array_equal(h_cnt8, d_cnt8.cpu().numpy()) and np.array_equal(h_desc[0, : len(kpf)], descf)
     s.close()
 
 
