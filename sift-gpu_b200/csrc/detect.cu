@@ -306,20 +306,32 @@ __global__ void __launch_bounds__(ORI_WARPS * 32) orientation_kernel(const __gri
         const int j_lo = max(-radius, 1 - px), j_hi = min(radius, cols - 2 - px);
         const int wj = j_hi - j_lo + 1;
         if (wj > 0 && i_lo <= i_hi) {
-            int ii = i_lo + lane / wj, jj = j_lo + lane % wj;  // flat raster index advanced by 32 without divisions
-            float2 cur = make_float2(0.f, 0.f);
-            if (ii <= i_hi) cur = __ldg(mo + (size_t)(py + ii) * pitch + (px + jj));
-            while (ii <= i_hi) {
-                int in = ii, jn = jj + 32;
-                while (jn > j_hi) { jn -= wj; ++in; }
-                float2 nxt = make_float2(0.f, 0.f);
-                if (in <= i_hi) nxt = __ldg(mo + (size_t)(py + in) * pitch + (px + jn));  // next sample's load overlaps this one's math
-                const float wgt = expf((ii * ii + jj * jj) * expf_scale);
-                int bin = cv_round((kOriBins / 360.f) * cur.y);
-                if (bin >= kOriBins) bin -= kOriBins;
-                if (bin < 0) bin += kOriBins;
-                priv[bin * 32] += wgt * cur.x;
-                ii = in; jj = jn; cur = nxt;
+            // flat raster index over the clipped window, 4 samples per lane per iteration: the four gradient-map loads are issued
+            // back to back (the kernel is bound by gather latency, not arithmetic); votes then go to the lane-private bins in order
+            const int total = (i_hi - i_lo + 1) * wj;
+            const float2* base = mo + (size_t)py * pitch + px;
+            int ci = i_lo + lane / wj, cj = j_lo + lane % wj;  // running (row, col) of this lane's next sample, advanced by 32 without divisions
+            for (int idx0 = lane; idx0 < total; idx0 += 128) {
+                int ii[4], jj[4];
+                float2 g[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    ii[u] = ci; jj[u] = cj;
+                    g[u] = make_float2(0.f, 0.f);
+                    if (idx0 + 32 * u < total) g[u] = __ldg(base + (ptrdiff_t)ci * pitch + cj);
+                    cj += 32;
+                    while (cj > j_hi) { cj -= wj; ++ci; }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (idx0 + 32 * u < total) {
+                        const float wgt = expf((ii[u] * ii[u] + jj[u] * jj[u]) * expf_scale);
+                        int bin = cv_round((kOriBins / 360.f) * g[u].y);
+                        if (bin >= kOriBins) bin -= kOriBins;
+                        if (bin < 0) bin += kOriBins;
+                        priv[bin * 32] += wgt * g[u].x;
+                    }
+                }
             }
         }
         (void)w;
