@@ -139,46 +139,54 @@ __device__ void calc_descriptor(const float2* __restrict__ mo, int rows, int col
                 st.mo = __ldg(rowp + min(st.j, jmax));  // clamped: always an interior pixel
             }
         };
+        // one step: the eight trilinear votes of the sample of this lane (position/metadata/gradient in st)
+        auto vote = [&](const Step& st) {
+            const int j = st.j, jhi_c = st.jhi;
+            const float isin_c = st.isin, icos_c = st.icos;
+            const float2 cur = st.mo;
+            {
+            const float c_rot = j * cos_t - isin_c;
+            const float r_rot = j * sin_t + icos_c;
+            float rbin = r_rot + DW / 2 - 0.5f;
+            float cbin = c_rot + DW / 2 - 0.5f;
+            const bool acc = j <= jhi_c && rbin > -1 && rbin < DW && cbin > -1 && cbin < DW;  // (:620)
+            const float w_ = expf((c_rot * c_rot + r_rot * r_rot) * exp_scale);
+            float obin = (cur.y - ori) * bins_per_rad;
+            const float mag = cur.x * w_;
+            const int r0 = cv_floor(rbin), c0 = cv_floor(cbin);
+            int o0 = cv_floor(obin);
+            rbin -= r0; cbin -= c0; obin -= o0;
+            if (o0 < 0) o0 += DB;
+            if (o0 >= DB) o0 -= DB;
+            const int la = r0 - 2 * p;  // local cell-row of the r0 vote; the r0+1 vote goes to la+1
+            if (acc && mag != 0.f && la >= -1 && la <= 1) {
+                // trilinear split in the reference's operation order (:656-662); votes for cells outside this pair or
+                // outside the 4x4 grid land in the thread's trash bin, so the eight updates are branch-free
+                const float v_r1 = mag * rbin, v_r0 = mag - v_r1;
+                const float v_rc11 = v_r1 * cbin, v_rc10 = v_r1 - v_rc11;
+                const float v_rc01 = v_r0 * cbin, v_rc00 = v_r0 - v_rc01;
+                const bool r_lo = la >= 0, r_hi = la <= 0, c_lo = c0 >= 0, c_hi = c0 <= DW - 2;
+                const int b00 = (la * DW + c0) * (DB + 1) + o0;  // bin of (r0, c0, o0)
+                const int i00 = r_lo && c_lo ? b00 : TRASH, i01 = r_lo && c_hi ? b00 + (DB + 1) : TRASH;
+                const int i10 = r_hi && c_lo ? b00 + DW * (DB + 1) : TRASH, i11 = r_hi && c_hi ? b00 + (DW + 1) * (DB + 1) : TRASH;
+                float v1;
+                v1 = v_rc00 * obin; priv[i00 * DT] += v_rc00 - v1; priv[(i00 + 1) * DT] += v1;
+                v1 = v_rc01 * obin; priv[i01 * DT] += v_rc01 - v1; priv[(i01 + 1) * DT] += v1;
+                v1 = v_rc10 * obin; priv[i10 * DT] += v_rc10 - v1; priv[(i10 + 1) * DT] += v1;
+                v1 = v_rc11 * obin; priv[i11 * DT] += v_rc11 - v1; priv[(i11 + 1) * DT] += v1;
+            }
+        }
+        };
+        // ring of three stages, unrolled by three so that a stage is refilled in place (no register shuffling)
         Step s0, s1, s2;
         issue(s0); issue(s1); issue(s2);
-        while (s0.ok) {
-            const int j = s0.j, jhi_c = s0.jhi;
-            const float isin_c = s0.isin, icos_c = s0.icos;
-            const float2 cur = s0.mo;
-            s0 = s1; s1 = s2;
-            issue(s2);
-            {
-                const float c_rot = j * cos_t - isin_c;
-                const float r_rot = j * sin_t + icos_c;
-                float rbin = r_rot + DW / 2 - 0.5f;
-                float cbin = c_rot + DW / 2 - 0.5f;
-                const bool acc = j <= jhi_c && rbin > -1 && rbin < DW && cbin > -1 && cbin < DW;  // (:620)
-                const float w_ = expf((c_rot * c_rot + r_rot * r_rot) * exp_scale);
-                float obin = (cur.y - ori) * bins_per_rad;
-                const float mag = cur.x * w_;
-                const int r0 = cv_floor(rbin), c0 = cv_floor(cbin);
-                int o0 = cv_floor(obin);
-                rbin -= r0; cbin -= c0; obin -= o0;
-                if (o0 < 0) o0 += DB;
-                if (o0 >= DB) o0 -= DB;
-                const int la = r0 - 2 * p;  // local cell-row of the r0 vote; the r0+1 vote goes to la+1
-                if (acc && mag != 0.f && la >= -1 && la <= 1) {
-                    // trilinear split in the reference's operation order (:656-662); votes for cells outside this pair or
-                    // outside the 4x4 grid land in the thread's trash bin, so the eight updates are branch-free
-                    const float v_r1 = mag * rbin, v_r0 = mag - v_r1;
-                    const float v_rc11 = v_r1 * cbin, v_rc10 = v_r1 - v_rc11;
-                    const float v_rc01 = v_r0 * cbin, v_rc00 = v_r0 - v_rc01;
-                    const bool r_lo = la >= 0, r_hi = la <= 0, c_lo = c0 >= 0, c_hi = c0 <= DW - 2;
-                    const int b00 = (la * DW + c0) * (DB + 1) + o0;  // bin of (r0, c0, o0)
-                    const int i00 = r_lo && c_lo ? b00 : TRASH, i01 = r_lo && c_hi ? b00 + (DB + 1) : TRASH;
-                    const int i10 = r_hi && c_lo ? b00 + DW * (DB + 1) : TRASH, i11 = r_hi && c_hi ? b00 + (DW + 1) * (DB + 1) : TRASH;
-                    float v1;
-                    v1 = v_rc00 * obin; priv[i00 * DT] += v_rc00 - v1; priv[(i00 + 1) * DT] += v1;
-                    v1 = v_rc01 * obin; priv[i01 * DT] += v_rc01 - v1; priv[(i01 + 1) * DT] += v1;
-                    v1 = v_rc10 * obin; priv[i10 * DT] += v_rc10 - v1; priv[(i10 + 1) * DT] += v1;
-                    v1 = v_rc11 * obin; priv[i11 * DT] += v_rc11 - v1; priv[(i11 + 1) * DT] += v1;
-                }
-            }
+        for (;;) {
+            if (!s0.ok) break;
+            vote(s0); issue(s0);
+            if (!s1.ok) break;
+            vote(s1); issue(s1);
+            if (!s2.ok) break;
+            vote(s2); issue(s2);
         }
         __syncthreads();
     }
