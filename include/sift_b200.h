@@ -89,6 +89,11 @@ int sift_b200_detect_describe_batch_host_u8(SiftB200* h, const uint8_t* imgs, in
 int sift_b200_detect_describe_batch_dev_u8(SiftB200* h, const uint8_t* d_imgs, int n_frames, int rows, int cols,
                                            SiftKeypoint* d_kp, float* d_desc, int* d_counts, int cap, void* stream);
 
+/* The driver's colour front end (src/main.cpp:84): cvtColor(COLOR_RGB2GRAY) applied to the interleaved BGR bytes imread
+ * returns -- channel 0 takes the "R" weight -- in cv2 4.13's 15-bit fixed point.  d_bgr [n_frames][rows][cols][3] u8 ->
+ * d_gray [n_frames][rows][cols] u8 (feed it to ..._batch_dev_u8), asynchronous on `stream`. */
+int sift_b200_rgb2gray_u8_dev(SiftB200* h, const uint8_t* d_bgr, int n_frames, int rows, int cols, uint8_t* d_gray, void* stream);
+
 /* 2x bilinear upsample front end (BASELINE config 3; the reference ignores doubleSize, src/sift.cpp:219-227, so this is an
  * extension with cv::resize(INTER_LINEAR) semantics: half-pixel centres, edge replicate).
  * Device: d_src [n_frames][rows][cols] -> d_dst [n_frames][2*rows][2*cols], asynchronous on `stream`; feed d_dst to

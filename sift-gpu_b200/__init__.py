@@ -29,7 +29,7 @@ OK, ERR_CAPACITY, ERR_ARG, ERR_CUDA, ERR_TOO_SMALL, ERR_ASSERT = range(6)
 ABI_SYMBOLS = [
     "sift_b200_last_error", "sift_b200_version", "sift_b200_create", "sift_b200_destroy",
     "sift_b200_detect_describe", "sift_b200_detect_describe_batch_dev", "sift_b200_detect_describe_batch_host",
-    "sift_b200_detect_describe_batch_host_u8", "sift_b200_detect_describe_batch_dev_u8", "sift_b200_upsample2x_dev", "sift_b200_detect_describe_up2", "sift_b200_gaussian_blur", "sift_b200_gaussian_blur_1d",
+    "sift_b200_detect_describe_batch_host_u8", "sift_b200_detect_describe_batch_dev_u8", "sift_b200_rgb2gray_u8_dev", "sift_b200_upsample2x_dev", "sift_b200_detect_describe_up2", "sift_b200_gaussian_blur", "sift_b200_gaussian_blur_1d",
     "sift_b200_build_gaussian_pyramid", "sift_b200_build_dog_pyramid", "sift_b200_find_scale_space_extrema",
     "sift_b200_cal_descriptor", "sift_b200_match_knn2", "sift_b200_launch_count", "sift_b200_set_stage_timing",
     "sift_b200_get_stage_ms",
@@ -143,6 +143,11 @@ class Sift:
     def detect_describe_batch_host_ptr(self, imgs_ptr: int, n: int, rows: int, cols: int, kp_ptr: int, desc_ptr: int, counts_ptr: int, cap: int):
         return self._check(lib().sift_b200_detect_describe_batch_host(self._h, C.c_void_p(imgs_ptr), n, rows, cols, C.c_void_p(kp_ptr), C.c_void_p(desc_ptr),
                                                                       C.c_void_p(counts_ptr), cap), allow=(ERR_CAPACITY,))
+
+    def rgb2gray_u8_dev(self, d_bgr, d_gray, stream: int = 0):
+        """src/main.cpp:84 colour front end on device tensors: uint8 [N,H,W,3] -> uint8 [N,H,W]."""
+        n, rows, cols, _ = d_bgr.shape
+        self._check(lib().sift_b200_rgb2gray_u8_dev(self._h, C.c_void_p(d_bgr.data_ptr()), n, rows, cols, C.c_void_p(d_gray.data_ptr()), C.c_void_p(stream)))
 
     def detect_describe_batch_host_u8_ptr(self, imgs_ptr: int, n: int, rows: int, cols: int, kp_ptr: int, desc_ptr: int, counts_ptr: int, cap: int):
         return self._check(lib().sift_b200_detect_describe_batch_host_u8(self._h, C.c_void_p(imgs_ptr), n, rows, cols, C.c_void_p(kp_ptr), C.c_void_p(desc_ptr),

@@ -474,6 +474,14 @@ int sift_b200_detect_describe(SiftB200* h, const float* img, int rows, int cols,
     return status;
 }
 
+int sift_b200_rgb2gray_u8_dev(SiftB200* h, const uint8_t* d_bgr, int n_frames, int rows, int cols, uint8_t* d_gray, void* stream) {
+    if (!h || !d_bgr || !d_gray || rows < 1 || cols < 1 || n_frames < 0) return fail(SIFT_B200_ERR_ARG, "bad argument");
+    CUDA_TRY(cudaSetDevice(h->device));
+    h->launches += launch_rgb2gray_u8(d_bgr, d_gray, (size_t)n_frames * rows * cols, (cudaStream_t)stream);
+    CUDA_TRY(cudaGetLastError());
+    return SIFT_B200_OK;
+}
+
 int sift_b200_upsample2x_dev(SiftB200* h, const float* d_src, int n_frames, int rows, int cols, float* d_dst, void* stream) {
     if (!h || !d_src || !d_dst || rows < 1 || cols < 1 || n_frames < 0) return fail(SIFT_B200_ERR_ARG, "bad argument");
     CUDA_TRY(cudaSetDevice(h->device));

@@ -142,8 +142,9 @@ struct OctArgs {
     size_t nframe_stride;
 };
 
-// One CTA per tile, 3 CTAs per SM.  (A persistent variant that kept the next tile's loads in flight in registers was
-// measured slower: 128 registers -> 2 CTAs/SM cost more than the exposed load latency it removed; profiles/README.md.)
+// One CTA per tile, 3 CTAs per SM.  Two variants were measured slower and dropped (profiles/README.md): a persistent CTA that
+// kept the next tile's loads in flight in registers (128 registers -> 2 CTAs/SM, 46.7 us), and a CTA marching down four blocks
+// re-using the last 2R horizontal-pass rows (13 % fewer FFMAs but spills, an extra barrier and a row shift per block: 46 us).
 __global__ void __launch_bounds__(NT, 3) octave_kernel(const OctArgs a) {
     extern __shared__ float smem[];
     float* sIn = smem;
@@ -281,6 +282,16 @@ __global__ void upsample2x_kernel(const float* __restrict__ src, float* __restri
     dst[(size_t)blockIdx.z * dst_fs + (size_t)y * (2 * cols) + x] = __fadd_rn(__fmul_rn(h0, b0), __fmul_rn(h1, b1));
 }
 
+// ---- driver's colour conversion (src/main.cpp:84): cvtColor(img, gray, COLOR_RGB2GRAY) applied to the BGR bytes imread returns,
+// i.e. channel 0 gets the "R" weight.  cv2 4.13 fixed point: (9798*c0 + 19235*c1 + 3735*c2 + 16384) >> 15  (OpenCV
+// 4.0 used the 14-bit table -- the tests pin the wheel that is available).  Interleaved 3-byte pixels in, dense u8 gray out.
+__global__ void rgb2gray_u8_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, size_t n_pixels) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pixels) return;
+    const uint8_t* p = src + 3 * i;
+    dst[i] = (uint8_t)((9798u * p[0] + 19235u * p[1] + 3735u * p[2] + 16384u) >> 15);
+}
+
 __global__ void dog_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ d, size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) d[i] = b[i] - a[i];
@@ -342,6 +353,11 @@ int launch_generic_blur(const float* src, float* dst, int rows, int cols, const 
 int launch_upsample2x(const float* src, float* dst, int rows, int cols, int n_frames, cudaStream_t st) {
     dim3 blk(32, 8), grid((2 * cols + 31) / 32, (2 * rows + 7) / 8, n_frames);
     upsample2x_kernel<<<grid, blk, 0, st>>>(src, dst, rows, cols, (size_t)rows * cols, (size_t)rows * cols * 4);
+    return 1;
+}
+
+int launch_rgb2gray_u8(const uint8_t* src, uint8_t* dst, size_t n_pixels, cudaStream_t st) {
+    rgb2gray_u8_kernel<<<(unsigned)((n_pixels + 255) / 256), 256, 0, st>>>(src, dst, n_pixels);
     return 1;
 }
 

@@ -81,6 +81,7 @@ int launch_base_blur(const float* src, size_t src_frame_stride, int src_pitch, c
 int launch_octave(const PyrView& pv, int o, int n_frames, bool write_all_levels, cudaStream_t st);
 int launch_generic_blur(const float* src, float* dst, int rows, int cols, const float* d_taps, int radius, int taps_hi, cudaStream_t st);
 int launch_dog(const PyrView& pv, int n_frames, cudaStream_t st);
+int launch_rgb2gray_u8(const uint8_t* src, uint8_t* dst, size_t n_pixels, cudaStream_t st);
 int launch_upsample2x(const float* src, float* dst, int rows, int cols, int n_frames, cudaStream_t st);
 int launch_gradient(const PyrView& pv, int n_frames, cudaStream_t st);
 int launch_extrema(const PyrView& pv, const DetectBuf& db, int n_frames, cudaStream_t st);

@@ -165,3 +165,30 @@ def test_upsample_front_end_and_config3(pkg, oracle, synth):
     frac, explained, unexplained, mx = parity.descriptor_report(desc[pi], odesc[pj], opq[pj])
     assert frac >= 0.93 and unexplained <= len(pairs) // 200, (frac, explained, unexplained, mx)
     s.close()
+
+
+def test_driver_colour_front_end(pkg, synth):
+    """src/main.cpp:84 applies COLOR_RGB2GRAY to BGR bytes; the GPU front end reproduces cv2's fixed point
+    exactly and feeds the u8 pipeline."""
+    import torch
+
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(3)
+    base = np.clip(np.rint(synth.recipe_s(320, 200, seed=6, blobs_per_1080p=20000)), 0, 255).astype(np.uint8)
+    bgr = np.stack([base, np.roll(base, 3, 1), rng.integers(0, 256, base.shape, dtype=np.uint8)], axis=-1)[None]
+    want = cv2.cvtColor(bgr[0], cv2.COLOR_RGB2GRAY)
+    s = pkg.Sift(200, 320, max_batch=1, max_kp_per_frame=4096)
+    d_bgr = torch.from_numpy(bgr).cuda()
+    d_gray = torch.zeros((1, 200, 320), dtype=torch.uint8, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    s.rgb2gray_u8_dev(d_bgr, d_gray, st)
+    torch.cuda.synchronize()
+    assert np.array_equal(d_gray[0].cpu().numpy(), want)
+    cap = 4096
+    d_kp = torch.zeros((1, cap, 28), dtype=torch.uint8, device="cuda"); d_desc = torch.zeros((1, cap, 128), device="cuda")
+    d_cnt = torch.zeros(1, dtype=torch.int32, device="cuda")
+    s.detect_describe_batch_dev(d_gray, d_kp, d_desc, d_cnt, cap, st)
+    torch.cuda.synchronize()
+    kp, desc = s.detect_describe(want.astype(np.float32))  # gray.convertTo(CV_32FC1): plain cast (src/main.cpp:85)
+    assert int(d_cnt[0]) == len(kp) > 20 and np.array_equal(d_desc[0, : len(kp)].cpu().numpy(), desc)
+    s.close()
