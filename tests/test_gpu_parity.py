@@ -149,3 +149,25 @@ def test_matcher_identical_indices(sift, pkg, oracle, golden):
         gi, gd, gg = sift.match_knn2(q, tr, norm)
         oi, od, og = oracle.match_knn2(q, tr, norm)
         assert np.array_equal(gi, oi) and np.array_equal(gg, og) and np.allclose(gd, od, rtol=1e-6)
+
+
+def test_config5_query_vs_scene_end_to_end(sift, pkg, golden):
+    """BASELINE config 5 as src/main.cpp runs it: scene (1st argument, resized 960x960) and query (native 2448x2448) through
+    detect+describe, then knnMatch(query, scene, 2) + ratio 0.86 (:23-40), everything on the GPU.  The matcher is index-exact on
+    identical inputs (test_matcher_identical_indices); here its inputs are the GPU's own descriptors, which differ from the
+    reference's by rare +-1 LSB quantisation flips, so a few near-tie rows may pick another neighbour: >= 97 % of the best
+    matches and >= 95 % of the ratio-test survivors must coincide with the reference fixture (observed ~99 %)."""
+    z = golden("match_query_scene")
+    scene = golden("scene_960")
+    kq, dq = sift.detect_describe(golden("query_2448")["gray"].astype(np.float32))
+    ks, ds = sift.detect_describe(scene["gray"].astype(np.float32))
+    assert len(kq) == len(z["query_kp"]) and len(ks) == len(scene["keypoints"])  # same keypoints, same order
+    for norm in (pkg.NORM_L1, pkg.NORM_L2):
+        idx, dist, good = sift.match_knn2(dq, ds, norm, 0.86)
+        same_best = np.mean(idx[:, 0] == z[f"idx_n{norm}"][:, 0])
+        ref_good = z[f"good_n{norm}"]
+        jacc = np.sum(good & ref_good) / max(1, np.sum(good | ref_good))
+        assert same_best >= 0.97 and jacc >= 0.95, (norm, same_best, jacc)
+        # accepted matches that both agree on point to the same scene keypoint
+        both = good & ref_good
+        assert np.mean(idx[both, 0] == z[f"idx_n{norm}"][both, 0]) >= 0.99
