@@ -8,10 +8,10 @@
 // needs shared-memory float atomics, which on sm_100a are CAS loops (ATOMS.CAST.SPIN) that serialise badly because
 // neighbouring samples hit the same bins.  This kernel is atomics-free and deterministic, one CTA (128 threads) per
 // keypoint, one pass:
-//   - the 4 cell-rows of the descriptor grid are split in two pairs p (a in {2p, 2p+1}); an 8-lane group owns (pair, window
+//   - the 4 cell-rows of the descriptor grid are split in two pairs p (a in {2p, 2p+1}); a 4-lane group owns (pair, window
 //     row): its lanes walk the row's j-interval 2p-1 <= rbin < 2p+2, -1 < cbin < 4 (two slab inequalities rounded
 //     outwards; the reference's exact test decides), one sample per lane per step with the next step's load already in
-//     flight; lanes of a group read consecutive pixels (coalesced 64-byte segments);
+//     flight; lanes of a group read consecutive pixels (coalesced 32-byte segments);
 //   - each sample reads {Mag, Ori} of its pixel from the level's gradient map (detect.cu: gradient_kernel, the reference's
 //     own per-sample arithmetic done once per pixel), applies the Gaussian weight, and its trilinear votes that fall into the pair's cells go straight into THREAD-PRIVATE histograms
 //     [2 cell-rows][4 cells][9 bins] in shared memory (layout [bin][thread]: conflict-free plain read-modify-write).
@@ -26,6 +26,10 @@ namespace {
 
 constexpr int DW = 4, DB = 8;  // SIFT_DESCR_WIDTH, SIFT_DESCR_HIST_BINS (src/sift.cpp:12,15)
 constexpr int DT = 128;        // threads per CTA = output elements
+#ifndef DESC_GL
+#define DESC_GL 4
+#endif
+constexpr int GL = DESC_GL;    // lanes per group (a group walks one window row of one cell-row pair); measured 2/4/8: 69.7/66.3/69.1 us
 constexpr int PRIV_BINS = 2 * DW * (DB + 1);      // private histogram of one thread: [2 cell-rows][4 cells][9 bins]
 constexpr int TRASH = PRIV_BINS;                   // private trash bins that swallow votes for cells outside the pair / the 4x4 grid
 constexpr int PRIV_FLOATS = (PRIV_BINS + 2) * DT;  // + two trash rows (a vote updates bins i and i+1)
@@ -89,8 +93,8 @@ __device__ void calc_descriptor(const float2* __restrict__ mo, int rows, int col
     const int imin = max(-radius, 1 - py), imax = min(radius, rows - 2 - py);   // 0 < r < rows-1
 
     for (int k = tid * 4; k < PRIV_FLOATS; k += DT * 4) *reinterpret_cast<float4*>(s_priv + k) = make_float4(0.f, 0.f, 0.f, 0.f);
-    const int gl = tid & 7;
-    const int p = tid >> 6, slot = (tid >> 3) & 7;  // cell-row pair (its 64 threads are contiguous), row slot (8 slots per pair)
+    const int gl = tid & (GL - 1);
+    const int p = tid >> 6, slot = (tid & 63) / GL;  // cell-row pair (its 64 threads are contiguous), row slot (64/GL slots per pair)
     float* priv = s_priv + tid;
     for (int band0 = imin; band0 <= imax; band0 += NB) {
         const int nrows = min(NB, imax - band0 + 1);
@@ -109,15 +113,15 @@ __device__ void calc_descriptor(const float2* __restrict__ mo, int rows, int col
         // flattened walk: a group advances through its rows (slot, slot+8, ...) one 8-sample step per iteration (one sample per
         // lane), so the four groups of a warp never wait for each other at row boundaries; the NEXT step's gradient-map load is
         // issued before the current step's arithmetic (software pipeline).
-        int r = slot - DT / 16, jb = 1, jhi = 0;
+        int r = slot - 64 / GL, jb = 1, jhi = 0;
         const float2* rowp = mo;
         float isin = 0.f, icos = 0.f;
         // advance (r, jb, jhi, rowp, isin, icos) to the next step; false when the group has no more work in this band
         auto advance = [&]() -> bool {
-            jb += 8;
+            jb += GL;
             if (jb > jhi) {
                 do {
-                    r += DT / 16;
+                    r += 64 / GL;
                     if (r >= nrows) return false;
                     jb = s_jlo[p * NB + r];
                     jhi = s_jhi[p * NB + r];
