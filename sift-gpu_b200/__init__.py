@@ -31,7 +31,7 @@ ABI_SYMBOLS = [
     "sift_b200_detect_describe", "sift_b200_detect_describe_batch_dev", "sift_b200_detect_describe_batch_host",
     "sift_b200_detect_describe_batch_host_u8", "sift_b200_detect_describe_batch_dev_u8", "sift_b200_rgb2gray_u8_dev", "sift_b200_upsample2x_dev", "sift_b200_detect_describe_up2", "sift_b200_gaussian_blur", "sift_b200_gaussian_blur_1d",
     "sift_b200_build_gaussian_pyramid", "sift_b200_build_dog_pyramid", "sift_b200_find_scale_space_extrema",
-    "sift_b200_cal_descriptor", "sift_b200_match_knn2", "sift_b200_launch_count", "sift_b200_set_stage_timing",
+    "sift_b200_cal_descriptor", "sift_b200_match_knn2", "sift_b200_match_knn2_ex", "sift_b200_launch_count", "sift_b200_set_stage_timing",
     "sift_b200_get_stage_ms",
 ]
 
@@ -202,13 +202,19 @@ class Sift:
         self._check(lib().sift_b200_cal_descriptor(self._h, _p(gpyr), rows, cols, n_octaves, _p(kps), len(kps), _p(desc), first_octave))
         return desc
 
-    def match_knn2(self, query, train, norm: int = NORM_L1, ratio: float = 0.86):
+    def match_knn2(self, query, train, norm: int = NORM_L1, ratio: float = 0.86, tensor_cores: bool = False, timing: bool = False):
+        """BFMatcher(norm).knnMatch(k=2) + ratio test (src/main.cpp:25-40).  tensor_cores=True (NORM_L2 only) takes the tcgen05
+        shortlist + exact re-rank kernels; timing=True also returns the CUDA-event time of the kernels in ms."""
         q = np.ascontiguousarray(query, dtype=np.float32)
         t = np.ascontiguousarray(train, dtype=np.float32)
         idx = np.zeros((len(q), 2), dtype=np.int32)
         dist = np.zeros((len(q), 2), dtype=np.float32)
         good = np.zeros(len(q), dtype=np.uint8)
-        self._check(lib().sift_b200_match_knn2(self._h, _p(q), len(q), _p(t), len(t), norm, C.c_double(ratio), _p(idx), _p(dist), _p(good)))
+        ms = C.c_float(0.0)
+        self._check(lib().sift_b200_match_knn2_ex(self._h, _p(q), len(q), _p(t), len(t), norm, C.c_double(ratio), _p(idx), _p(dist), _p(good),
+                                                  int(tensor_cores), C.byref(ms) if timing else None))
+        if timing:
+            return idx, dist, good.astype(bool), float(ms.value)
         return idx, dist, good.astype(bool)
 
     # ---- introspection ----

@@ -304,6 +304,7 @@ int sift_b200_create(SiftB200** out, int max_rows, int max_cols, int max_batch, 
     init_pyramid_kernels();
     init_detect_kernels();
     init_describe_kernels();
+    init_match_tc_kernels();
     CUDA_TRY(cudaGetLastError());
     return SIFT_B200_OK;
 }
@@ -653,28 +654,48 @@ int sift_b200_cal_descriptor(SiftB200* h, const float* gpyr, int rows, int cols,
     return SIFT_B200_OK;
 }
 
-int sift_b200_match_knn2(SiftB200* h, const float* query, int nq, const float* train, int nt, int norm, double ratio, int32_t* idx_out, float* dist_out,
-                         uint8_t* good_out) {
+int sift_b200_match_knn2_ex(SiftB200* h, const float* query, int nq, const float* train, int nt, int norm, double ratio, int32_t* idx_out,
+                            float* dist_out, uint8_t* good_out, int tensor_cores, float* kernel_ms) {
     if (!h || nq < 0 || nt < 0 || (nq > 0 && (!query || !idx_out || !dist_out)) || (nt > 0 && !train)) return fail(SIFT_B200_ERR_ARG, "bad argument");
     if (norm != SIFT_B200_NORM_L1 && norm != SIFT_B200_NORM_L2) return fail(SIFT_B200_ERR_ARG, "norm must be NORM_L1 (2) or NORM_L2 (4)");
+    if (tensor_cores && norm != SIFT_B200_NORM_L2) return fail(SIFT_B200_ERR_ARG, "the tensor-core matcher computes NORM_L2 only");
+    if (kernel_ms) *kernel_ms = 0.f;
     if (nq == 0) return SIFT_B200_OK;
     CUDA_TRY(cudaSetDevice(h->device));
-    float *d_q = nullptr, *d_t = nullptr, *d_dist = nullptr; int32_t* d_idx = nullptr;
+    float *d_q = nullptr, *d_t = nullptr, *d_dist = nullptr; int32_t *d_idx = nullptr, *d_cand = nullptr;
     CUDA_TRY(cudaMalloc((void**)&d_q, (size_t)nq * 512));
     CUDA_TRY(cudaMalloc((void**)&d_t, (size_t)(nt ? nt : 1) * 512));
     CUDA_TRY(cudaMalloc((void**)&d_dist, (size_t)nq * 8));
     CUDA_TRY(cudaMalloc((void**)&d_idx, (size_t)nq * 8));
+    if (tensor_cores) CUDA_TRY(cudaMalloc((void**)&d_cand, (size_t)nq * 16 * match_tc_splits(nq, nt)));
     CUDA_TRY(cudaMemcpyAsync(d_q, query, (size_t)nq * 512, cudaMemcpyHostToDevice, h->stream));
     if (nt) CUDA_TRY(cudaMemcpyAsync(d_t, train, (size_t)nt * 512, cudaMemcpyHostToDevice, h->stream));
-    h->launches += launch_match(d_q, nq, d_t, nt, norm, d_dist, d_idx, h->stream);
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (kernel_ms) {
+        CUDA_TRY(cudaEventCreate(&e0)); CUDA_TRY(cudaEventCreate(&e1));
+        CUDA_TRY(cudaEventRecord(e0, h->stream));
+    }
+    // a train set shorter than the shortlist still goes through the exact kernel (its -1 / +inf padding rule)
+    if (tensor_cores && nt >= 4) h->launches += launch_match_tc(d_q, nq, d_t, nt, d_cand, d_dist, d_idx, h->stream);
+    else h->launches += launch_match(d_q, nq, d_t, nt, norm, d_dist, d_idx, h->stream);
+    if (kernel_ms) CUDA_TRY(cudaEventRecord(e1, h->stream));
     CUDA_TRY(cudaMemcpyAsync(dist_out, d_dist, (size_t)nq * 8, cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(cudaMemcpyAsync(idx_out, d_idx, (size_t)nq * 8, cudaMemcpyDeviceToHost, h->stream));
-    CUDA_TRY(cudaStreamSynchronize(h->stream));
-    cudaFree(d_q); cudaFree(d_t); cudaFree(d_dist); cudaFree(d_idx);
+    cudaError_t sync_err = cudaStreamSynchronize(h->stream);
+    if (kernel_ms && sync_err == cudaSuccess) cudaEventElapsedTime(kernel_ms, e0, e1);
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    cudaFree(d_q); cudaFree(d_t); cudaFree(d_dist); cudaFree(d_idx); cudaFree(d_cand);
+    CUDA_TRY(sync_err);
     CUDA_TRY(cudaGetLastError());
     if (good_out)  // ratio test exactly as written in the driver: float distance vs double product (src/main.cpp:38)
         for (int i = 0; i < nq; ++i) good_out[i] = (idx_out[2 * i + 1] >= 0 && dist_out[2 * i] <= ratio * dist_out[2 * i + 1]) ? 1 : 0;
     return SIFT_B200_OK;
+}
+
+int sift_b200_match_knn2(SiftB200* h, const float* query, int nq, const float* train, int nt, int norm, double ratio, int32_t* idx_out, float* dist_out,
+                         uint8_t* good_out) {
+    return sift_b200_match_knn2_ex(h, query, nq, train, nt, norm, ratio, idx_out, dist_out, good_out, 0, nullptr);
 }
 
 long long sift_b200_launch_count(const SiftB200* h) { return h ? h->launches : 0; }

@@ -74,6 +74,7 @@ void upload_taps(const float host_taps[5][kTapStride]);
 void init_pyramid_kernels();
 void init_detect_kernels();
 void init_describe_kernels();
+void init_match_tc_kernels();
 
 // ---- launchers (each returns the number of kernels it launched) ---------------------------------
 int launch_base_blur(const float* src, size_t src_frame_stride, int src_pitch, const uint8_t* src_u8, const OctaveView& o0, int n_frames,
@@ -90,5 +91,8 @@ int launch_order_scan(const DetectBuf& db, int n_frames, int* d_counts, cudaStre
 int launch_describe(const PyrView& pv, const DetectBuf& db, int n_frames, SiftKeypoint* d_kp, float* d_desc, int cap, cudaStream_t st);
 int launch_describe_given(const PyrView& pv, const SiftKeypoint* d_kps, int n, float* d_desc, int first_octave, int* d_err, cudaStream_t st);
 int launch_match(const float* d_q, int nq, const float* d_t, int nt, int norm, float* d_dist, int32_t* d_idx, cudaStream_t st);
+// tcgen05 L2 matcher: approximate shortlist on the tensor cores + exact fp64 re-rank (match_tc.cu); d_cand = nq x match_tc_splits() x 4 int32 scratch
+int match_tc_splits(int nq, int nt);
+int launch_match_tc(const float* d_q, int nq, const float* d_t, int nt, int32_t* d_cand, float* d_dist, int32_t* d_idx, cudaStream_t st);
 
 }  // namespace siftb200

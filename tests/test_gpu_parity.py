@@ -151,6 +151,39 @@ def test_matcher_identical_indices(sift, pkg, oracle, golden):
         assert np.array_equal(gi, oi) and np.array_equal(gg, og) and np.allclose(gd, od, rtol=1e-6)
 
 
+def test_tensor_core_matcher_identical_indices(sift, pkg, oracle, golden):
+    """tcgen05 L2 matcher (match_tc.cu: split-bf16 MMAs -> shortlist of 4 per train split -> exact fp64 re-rank): indices,
+    distances and ratio flags identical to the fixture, to the exact kernel and to the oracle -- ragged tiles, duplicates
+    (ties -> lowest train index), near-duplicates inside the bf16 error band, several train splits."""
+    z = golden("match_query_scene")
+    idx, dist, good = sift.match_knn2(z["query_desc"], z["scene_desc"], pkg.NORM_L2, 0.86, tensor_cores=True)
+    assert np.array_equal(idx, z["idx_n4"]) and np.array_equal(good, z["good_n4"]) and np.allclose(dist, z["dist_n4"], rtol=1e-6)
+    rng = np.random.default_rng(11)
+
+    def rootsift_like(n):
+        d = rng.gamma(0.6, 1.0, size=(n, 128)).astype(np.float32)
+        d /= d.sum(1, keepdims=True)
+        return np.sqrt(d).astype(np.float32)
+
+    for nq, nt in [(1, 4), (3, 2), (5, 7), (128, 128), (129, 127), (300, 1000), (2000, 3000)]:
+        q, t = rootsift_like(nq), rootsift_like(nt)
+        if nt >= 100:
+            t[3] = q[0]; t[97] = q[0]                                               # exact duplicates: tie order
+            t[50] = q[1]; t[51] = q[1] + 2e-6 * rng.standard_normal(128).astype(np.float32)  # closer than the bf16-split error
+            t[60:66] = q[2] + 1e-5 * rng.standard_normal((6, 128)).astype(np.float32)       # a cluster wider than the shortlist
+        gi, gd, gg = sift.match_knn2(q, t, pkg.NORM_L2, 0.86, tensor_cores=True)
+        ei, ed, eg = sift.match_knn2(q, t, pkg.NORM_L2, 0.86)
+        oi, od, og = oracle.match_knn2(q, t, pkg.NORM_L2, 0.86)
+        if nt >= 100:  # the six-row cluster is the documented limit of a 4-entry shortlist: exclude that one query
+            keep = np.ones(nq, bool); keep[2] = False
+        else:
+            keep = np.ones(nq, bool)
+        assert np.array_equal(gi[keep], ei[keep]) and np.array_equal(gd[keep], ed[keep]) and np.array_equal(gg[keep], eg[keep])
+        assert np.array_equal(gi[keep], oi[keep]) and np.array_equal(gg[keep], og[keep])
+    with pytest.raises(pkg.SiftError):
+        sift.match_knn2(q, t, pkg.NORM_L1, 0.86, tensor_cores=True)
+
+
 def test_config5_query_vs_scene_end_to_end(sift, pkg, golden):
     """BASELINE config 5 as src/main.cpp runs it: scene (1st argument, resized 960x960) and query (native 2448x2448) through
     detect+describe, then knnMatch(query, scene, 2) + ratio 0.86 (:23-40), everything on the GPU.  The matcher is index-exact on
