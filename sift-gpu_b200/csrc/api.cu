@@ -51,12 +51,14 @@ struct SiftB200 {
     int* h_counts = nullptr;    // pinned
     // second staging set + copy streams for the pipelined host-batch entry point
     float* d_img2 = nullptr;
+    float* d_img3 = nullptr;  // third input buffer: lets the H2D copy run one chunk ahead of the two compute lanes
+    bool taper = true;        // host batch: short chunks at both ends of a call (env SIFT_B200_TAPER=0 disables)
     SiftKeypoint* d_kp2 = nullptr;
     float* d_desc2 = nullptr;
     int* d_counts2 = nullptr;
     int* h_counts2 = nullptr;
     cudaStream_t s_in = nullptr, s_out = nullptr;
-    cudaEvent_t ev_in[2] = {}, ev_comp[2] = {}, ev_cnt[2] = {}, ev_out[2] = {};
+    cudaEvent_t ev_in[3] = {}, ev_comp[3] = {}, ev_cnt[2] = {}, ev_out[2] = {};
     long long launches = 0;
     bool stage_timing = false;
     cudaEvent_t ev[9] = {};
@@ -291,6 +293,7 @@ int sift_b200_create(SiftB200** out, int max_rows, int max_cols, int max_batch, 
     const size_t F = max_batch;
     if (int rc_db = alloc_detectbuf(h->db, F, max_kp_per_frame)) return rc_db;
     if (const char* e = getenv("SIFT_B200_LANES")) h->lanes = atoi(e);
+    if (const char* e = getenv("SIFT_B200_TAPER")) h->taper = atoi(e) != 0;
     CUDA_TRY(cudaMalloc((void**)&h->d_counts, F * sizeof(int)));
     CUDA_TRY(cudaMallocHost((void**)&h->h_counts, F * sizeof(int)));
     for (auto& e : h->ev) CUDA_TRY(cudaEventCreate(&e));
@@ -321,9 +324,10 @@ int sift_b200_destroy(SiftB200* h) {
     for (auto& e : h->ev_join) if (e) cudaEventDestroy(e);
     cudaFree(h->d_img); cudaFree(h->d_kp); cudaFree(h->d_desc); cudaFree(h->d_counts);
     cudaFreeHost(h->h_counts);
-    cudaFree(h->d_img2); cudaFree(h->d_kp2); cudaFree(h->d_desc2); cudaFree(h->d_counts2);
+    cudaFree(h->d_img2); cudaFree(h->d_img3); cudaFree(h->d_kp2); cudaFree(h->d_desc2); cudaFree(h->d_counts2);
     if (h->h_counts2) cudaFreeHost(h->h_counts2);
-    for (int b = 0; b < 2; ++b) for (cudaEvent_t e : {h->ev_in[b], h->ev_comp[b], h->ev_cnt[b], h->ev_out[b]}) if (e) cudaEventDestroy(e);
+    for (int b = 0; b < 3; ++b) for (cudaEvent_t e : {h->ev_in[b], h->ev_comp[b]}) if (e) cudaEventDestroy(e);
+    for (int b = 0; b < 2; ++b) for (cudaEvent_t e : {h->ev_cnt[b], h->ev_out[b]}) if (e) cudaEventDestroy(e);
     if (h->s_in) cudaStreamDestroy(h->s_in);
     if (h->s_out) cudaStreamDestroy(h->s_out);
     for (auto& e : h->ev) if (e) cudaEventDestroy(e);
@@ -357,24 +361,42 @@ static int ensure_pipeline(SiftB200* h) {
     if (h->d_img2) return SIFT_B200_OK;
     const size_t F = h->max_batch;
     CUDA_TRY(cudaMalloc((void**)&h->d_img2, F * (size_t)h->max_rows * h->max_cols * sizeof(float)));
+    CUDA_TRY(cudaMalloc((void**)&h->d_img3, F * (size_t)h->max_rows * h->max_cols * sizeof(float)));
     CUDA_TRY(cudaMalloc((void**)&h->d_kp2, F * (size_t)h->cap_kp * sizeof(SiftKeypoint)));
     CUDA_TRY(cudaMalloc((void**)&h->d_desc2, F * (size_t)h->cap_kp * 128 * sizeof(float)));
     CUDA_TRY(cudaMalloc((void**)&h->d_counts2, F * sizeof(int)));
     CUDA_TRY(cudaMallocHost((void**)&h->h_counts2, F * sizeof(int)));
     CUDA_TRY(cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking));
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < 3; ++b) {
         CUDA_TRY(cudaEventCreateWithFlags(&h->ev_in[b], cudaEventDisableTiming));
         CUDA_TRY(cudaEventCreateWithFlags(&h->ev_comp[b], cudaEventDisableTiming));
+    }
+    for (int b = 0; b < 2; ++b) {
         CUDA_TRY(cudaEventCreateWithFlags(&h->ev_cnt[b], cudaEventDisableTiming));
         CUDA_TRY(cudaEventCreateWithFlags(&h->ev_out[b], cudaEventDisableTiming));
     }
     return SIFT_B200_OK;
 }
 
-// Host batch, software-pipelined over chunks of max_batch frames: H2D of chunk k+1 (stream s_in) and the exact-size
-// D2H of chunk k-1 (stream s_out) overlap the kernels of chunk k (h->stream).  The host only ever waits for the tiny
-// counts copy of the PREVIOUS chunk, after the next chunk's work has been queued, so the GPU never idles on the host.
+// Chunk schedule of one host-batch call.  The copy engines and the SMs only overlap in the steady state: the first chunk's H2D and
+// the last chunk's kernels + D2H run alone.  Short chunks at both ends (max_batch/8, /4, /2) shrink those two bubbles; the middle
+// runs full max_batch chunks, where the kernels are most efficient.
+static std::vector<int> chunk_plan(int n_frames, int max_batch, bool taper) {
+    std::vector<int> head, plan;
+    int rem = n_frames;
+    if (taper && n_frames >= 3 * max_batch)
+        for (int sz = max_batch / 8 > 0 ? max_batch / 8 : 1; sz < max_batch; sz *= 2) head.push_back(sz);
+    for (int sz : head) { plan.push_back(sz); rem -= 2 * sz; }
+    if (rem % max_batch) { plan.push_back(rem % max_batch); rem -= rem % max_batch; }
+    for (; rem > 0; rem -= max_batch) plan.push_back(max_batch);
+    for (size_t i = head.size(); i-- > 0;) plan.push_back(head[i]);
+    return plan;
+}
+
+// Host batch, software-pipelined over the chunks of chunk_plan(): the H2D of chunk k+1 (stream s_in, three input buffers) and the
+// exact-size D2H of chunk k-1 (stream s_out) overlap the kernels of chunk k, which alternate between the two compute lanes.  The
+// host only ever waits for the tiny counts copy of the PREVIOUS chunk, after the next chunk's copy and kernels have been queued.
 static int batch_host_impl(SiftB200* h, const void* imgs_v, int elem, int n_frames, int rows, int cols, SiftKeypoint* kp_out, float* desc_out,
                            int* counts_out, int cap) {
     const unsigned char* imgs = static_cast<const unsigned char*>(imgs_v);  // elem = 4 (float32 frames) or 1 (uint8 frames)
@@ -389,16 +411,25 @@ static int batch_host_impl(SiftB200* h, const void* imgs_v, int elem, int n_fram
     if (two && (rc = ensure_lane2(h))) return rc;
     cudaStream_t cst[2] = {h->stream, two ? h->stream2 : h->stream};  // chunk k computes in lane k&1
     const size_t fs = (size_t)rows * cols;
-    float* d_img[2] = {h->d_img, h->d_img2};
+    float* d_img[3] = {h->d_img, h->d_img2, h->d_img3};
     SiftKeypoint* d_kp[2] = {h->d_kp, h->d_kp2};
     float* d_desc[2] = {h->d_desc, h->d_desc2};
     int* d_cnt[2] = {h->d_counts, h->d_counts2};
     int* h_cnt[2] = {h->h_counts, h->h_counts2};
     int status = SIFT_B200_OK;
-    const int n_chunks = (n_frames + h->max_batch - 1) / h->max_batch;
+    const std::vector<int> plan = chunk_plan(n_frames, h->max_batch, h->taper);
+    const int n_chunks = (int)plan.size();
+    std::vector<int> first(n_chunks + 1, 0);
+    for (int k = 0; k < n_chunks; ++k) first[k + 1] = first[k] + plan[k];
+    auto copy_in = [&](int k) -> int {
+        const int ib = k % 3;
+        if (k >= 3) CUDA_TRY(cudaStreamWaitEvent(h->s_in, h->ev_comp[ib], 0));  // chunk k-3 has consumed this input buffer
+        CUDA_TRY(cudaMemcpyAsync(d_img[ib], imgs + (size_t)first[k] * fs * elem, plan[k] * fs * elem, cudaMemcpyHostToDevice, h->s_in));
+        CUDA_TRY(cudaEventRecord(h->ev_in[ib], h->s_in));
+        return SIFT_B200_OK;
+    };
     auto flush = [&](int k) -> int {  // exact-size D2H of chunk k once its counts are on the host
-        const int b = k & 1, f0 = k * h->max_batch;
-        const int nf = n_frames - f0 < h->max_batch ? n_frames - f0 : h->max_batch;
+        const int b = k & 1, f0 = first[k], nf = plan[k];
         CUDA_TRY(cudaEventSynchronize(h->ev_cnt[b]));
         for (int f = 0; f < nf; ++f) {
             int n = h_cnt[b][f];
@@ -413,21 +444,19 @@ static int batch_host_impl(SiftB200* h, const void* imgs_v, int elem, int n_fram
         CUDA_TRY(cudaEventRecord(h->ev_out[b], h->s_out));
         return SIFT_B200_OK;
     };
+    if (n_chunks > 0 && (rc = copy_in(0))) return rc;
     for (int k = 0; k < n_chunks; ++k) {
-        const int b = k & 1, f0 = k * h->max_batch;
-        const int nf = n_frames - f0 < h->max_batch ? n_frames - f0 : h->max_batch;
-        if (k >= 2) CUDA_TRY(cudaStreamWaitEvent(h->s_in, h->ev_comp[b], 0));   // chunk k-2 has consumed this input buffer
-        CUDA_TRY(cudaMemcpyAsync(d_img[b], imgs + (size_t)f0 * fs * elem, nf * fs * elem, cudaMemcpyHostToDevice, h->s_in));
-        CUDA_TRY(cudaEventRecord(h->ev_in[b], h->s_in));
-        CUDA_TRY(cudaStreamWaitEvent(cst[b], h->ev_in[b], 0));
+        const int b = k & 1, ib = k % 3, nf = plan[k];
+        if (k + 1 < n_chunks && (rc = copy_in(k + 1))) return rc;  // queued before the host blocks in flush() below
+        CUDA_TRY(cudaStreamWaitEvent(cst[b], h->ev_in[ib], 0));
         if (k >= 2) CUDA_TRY(cudaStreamWaitEvent(cst[b], h->ev_out[b], 0)); // chunk k-2's results have left this output buffer
-        rc = enqueue_chunk(h, two ? b : 0, elem == 4 ? d_img[b] : nullptr, elem == 1 ? reinterpret_cast<const uint8_t*>(d_img[b]) : nullptr, nf, rows, cols,
-                           d_kp[b], d_desc[b], d_cnt[b], cap, cst[b], false);
+        rc = enqueue_chunk(h, two ? b : 0, elem == 4 ? d_img[ib] : nullptr, elem == 1 ? reinterpret_cast<const uint8_t*>(d_img[ib]) : nullptr, nf, rows,
+                           cols, d_kp[b], d_desc[b], d_cnt[b], cap, cst[b], false);
         if (rc) return rc;
-        CUDA_TRY(cudaEventRecord(h->ev_comp[b], cst[b]));
+        CUDA_TRY(cudaEventRecord(h->ev_comp[ib], cst[b]));
         // results of chunk k-1 go out on s_out WHILE chunk k computes (queued before the wait on chunk k below)
         if (k >= 1 && (rc = flush(k - 1))) return rc;
-        CUDA_TRY(cudaStreamWaitEvent(h->s_out, h->ev_comp[b], 0));
+        CUDA_TRY(cudaStreamWaitEvent(h->s_out, h->ev_comp[ib], 0));
         CUDA_TRY(cudaMemcpyAsync(h_cnt[b], d_cnt[b], nf * sizeof(int), cudaMemcpyDeviceToHost, h->s_out));
         CUDA_TRY(cudaEventRecord(h->ev_cnt[b], h->s_out));
     }
