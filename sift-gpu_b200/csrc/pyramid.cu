@@ -5,21 +5,43 @@
 // (radius floor(3 sigma)) sampled 2-D Gaussian, zero padded, with source row rows-1 / col cols-1 read as
 // zero (:116).  That kernel and that mask are both separable, so each scale is two 1-D passes here.
 //
-// octave_kernel: one CTA owns a 32x64 output tile of one frame.
-//   phase 1  masked octave-base tile + 18-px halo  -> shared (coalesced 4-byte loads, odd pitch)
-//   phase 2  horizontal pass, 4 scales (radii 4/8/12/18), register-blocked: a thread produces 8 adjacent
-//            outputs of one row from 8+2r shared loads; lanes run down rows (odd pitch => conflict-free)
-//   phase 3  vertical pass, lane = column, 8 output rows per thread, all 4 scales kept in registers so the
-//            DoG subtraction, the G1/G2 stores and the NEAREST-decimated next-octave base (src[2y][2x],
-//            :253-254) are fused into the epilogue; every store is a full 128-byte row segment.
+// octave_kernel: one CTA owns a 32x64 output tile of one frame.  All arithmetic is packed FFMA2 (fma.rn.f32x2, new on
+// sm_100): the kernel is instruction-issue bound, and one FFMA2 issues two FMAs.  Both shared tiles are stored ROW-PAIR
+// INTERLEAVED -- element (y, x) lives in float2 [y/2][x], component y&1 -- so that an aligned register pair always holds
+// the same column of two adjacent rows.
+//   phase 1  masked octave-base tile + 18-px halo -> shared (16-byte global loads)
+//   phase 2  horizontal pass, 4 scales (radii 4/8/12/18): a thread produces 8 adjacent outputs for TWO rows from 8+2r
+//            8-byte shared loads; taps are broadcast uniform-register operands; lanes run down row pairs (odd pitch)
+//   phase 3  vertical pass, lane = column, 8 output rows (4 row pairs) per thread: even taps hit aligned input pairs
+//            (broadcast tap), odd taps are applied as a tap PAIR {t[2d-1], t[2d+1]} to the same input pair and land in a
+//            second, swapped accumulator; the two are added at the end.  All 4 scales stay in registers so the DoG
+//            subtraction, the G1/G2 stores and the NEAREST-decimated next-octave base (src[2y][2x], :253-254) are fused
+//            into the epilogue; every store is a full 128-byte row segment.
 // HBM traffic per pixel: 4 B read (+halo re-reads served by L2) and 28 B written (G1,G2,D0..D3, 1/4 G0').
 #include "sift_internal.cuh"
 
 namespace siftb200 {
 
+constexpr int kOddStride = 20;  // >= kMaxRadius + 1 tap pairs
 __constant__ float c_taps[5][kTapStride];
+__constant__ float2 c_odd[5][kOddStride];  // c_odd[s][d] = {t[2d-1], t[2d+1]} (zero outside the kernel)
 
-void upload_taps(const float host_taps[5][kTapStride]) { cudaMemcpyToSymbol(c_taps, host_taps, sizeof(float) * 5 * kTapStride); }
+namespace {
+__host__ __device__ constexpr int rad_of(int s) { return s <= 1 ? 4 : s == 2 ? 8 : s == 3 ? 12 : 18; }
+}  // namespace
+
+void upload_taps(const float host_taps[5][kTapStride]) {
+    cudaMemcpyToSymbol(c_taps, host_taps, sizeof(float) * 5 * kTapStride);
+    float2 odd[5][kOddStride] = {};
+    for (int s = 0; s < 5; ++s) {
+        const int R = rad_of(s);
+        for (int d = 0; d <= R; ++d) {
+            odd[s][d].x = d >= 1 ? host_taps[s][2 * d - 1] : 0.f;
+            odd[s][d].y = d < R ? host_taps[s][2 * d + 1] : 0.f;
+        }
+    }
+    cudaMemcpyToSymbol(c_odd, odd, sizeof(odd));
+}
 
 namespace {
 
@@ -27,39 +49,68 @@ constexpr int TW = 32;   // tile width  (= warp width: one lane per column in th
 constexpr int TH = 64;   // tile height
 constexpr int NT = 256;  // threads per CTA
 constexpr int GRP = 8;   // outputs per thread along the filter direction
-constexpr int HP = TW + 1;  // pitch of the horizontal-pass results (odd)
+constexpr int HP2 = TW + 1;  // pitch of the horizontal-pass results, in float2 (odd)
 
-__host__ __device__ constexpr int rad_of(int s) { return s <= 1 ? 4 : s == 2 ? 8 : s == 3 ? 12 : 18; }
+// element (y, x) of a row-pair-interleaved tile with pitch P2 (float2 per row pair)
+__device__ __forceinline__ int il_index(int y, int x, int P2) { return ((y >> 1) * P2 + x) * 2 + (y & 1); }
 
-// 8 outputs of a (2R+1)-tap FIR from 8+2R inputs at `in[t*stride]`; taps are compile-time constant-bank operands.
-template <int S, int STRIDE>
-__device__ __forceinline__ void fir8(const float* __restrict__ in, float (&acc)[GRP]) {
+// Horizontal: 8 adjacent outputs of a (2R+1)-tap FIR for two rows at once, from 8+2R float2 inputs.
+template <int S>
+__device__ __forceinline__ void fir8_rows2(const float2* __restrict__ in, float2 (&acc)[GRP]) {
     constexpr int R = rad_of(S);
 #pragma unroll
-    for (int k = 0; k < GRP; ++k) acc[k] = 0.f;
+    for (int k = 0; k < GRP; ++k) acc[k] = make_float2(0.f, 0.f);
 #pragma unroll
     for (int t = 0; t < GRP + 2 * R; ++t) {
-        const float v = in[t * STRIDE];
+        const float2 v = in[t];
 #pragma unroll
         for (int k = 0; k < GRP; ++k) {
             const int j = t - k;
-            if (j >= 0 && j <= 2 * R) acc[k] = fmaf(v, c_taps[S][j], acc[k]);
+            if (j >= 0 && j <= 2 * R) acc[k] = __ffma2_rn(v, make_float2(c_taps[S][j], c_taps[S][j]), acc[k]);
         }
     }
 }
 
-// Horizontal pass of scale S over the rows the vertical pass will need: [HALO-R, HALO+TH+R) of the input tile.
-template <int S, int HALO>
-__device__ __forceinline__ void hpass(const float* __restrict__ sIn, float* __restrict__ sH, int tid) {
+// Vertical: 8 consecutive output rows of one column.  `in` points at the input pair holding rows {r0 - R, r0 - R + 1} of the
+// column (r0 = first output row, even), pairs are HP2 apart.  out[r0+2j] = P[j].x + Q[j].y, out[r0+2j+1] = P[j].y + Q[j].x.
+template <int S>
+__device__ __forceinline__ void fir8_col(const float2* __restrict__ in, float (&g)[GRP]) {
     constexpr int R = rad_of(S);
-    constexpr int IP = TW + 2 * HALO + 1;
-    constexpr int NROWS = TH + 2 * R;
-    constexpr int NITEMS = NROWS * (TW / GRP);
+    float2 P[GRP / 2], Q[GRP / 2];
+#pragma unroll
+    for (int j = 0; j < GRP / 2; ++j) P[j] = Q[j] = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int m = 0; m < GRP / 2 + R; ++m) {
+        const float2 v = in[m * HP2];
+#pragma unroll
+        for (int j = 0; j < GRP / 2; ++j) {
+            const int d = m - j;
+            if (d >= 0 && d <= R) {
+                P[j] = __ffma2_rn(v, make_float2(c_taps[S][2 * d], c_taps[S][2 * d]), P[j]);
+                Q[j] = __ffma2_rn(v, c_odd[S][d], Q[j]);
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < GRP / 2; ++j) {
+        g[2 * j] = P[j].x + Q[j].y;
+        g[2 * j + 1] = P[j].y + Q[j].x;
+    }
+}
+
+// Horizontal pass of scale S over the rows the vertical pass will need: [HALO-R, HALO+TH+R) of the input tile (HALO-R even).
+template <int S, int HALO>
+__device__ __forceinline__ void hpass(const float2* __restrict__ sIn, float2* __restrict__ sH, int tid) {
+    constexpr int R = rad_of(S);
+    static_assert((HALO - R) % 2 == 0, "row pairs of the pass must be row pairs of the tile");
+    constexpr int IP2 = TW + 2 * HALO + 1;
+    constexpr int NPAIRS = (TH + 2 * R) / 2;
+    constexpr int NITEMS = NPAIRS * (TW / GRP);
     for (int id = tid; id < NITEMS; id += NT) {
-        const int row = id % NROWS, g = id / NROWS;
-        float acc[GRP];
-        fir8<S, 1>(sIn + (HALO - R + row) * IP + (HALO - R + GRP * g), acc);
-        float* out = sH + row * HP + GRP * g;
+        const int m = id % NPAIRS, g = id / NPAIRS;
+        float2 acc[GRP];
+        fir8_rows2<S>(sIn + ((HALO - R) / 2 + m) * IP2 + (HALO - R + GRP * g), acc);
+        float2* out = sH + m * HP2 + GRP * g;
 #pragma unroll
         for (int k = 0; k < GRP; ++k) out[k] = acc[k];
     }
@@ -70,7 +121,7 @@ __device__ __forceinline__ void hpass(const float* __restrict__ sIn, float* __re
 template <int HALO>
 __device__ __forceinline__ void load_tile(float* __restrict__ sIn, const float* __restrict__ src, const uint8_t* __restrict__ src8, int rows,
                                           int cols, int pitch, int ty0, int tx0, int tid) {
-    constexpr int IW = TW + 2 * HALO, IH = TH + 2 * HALO, IP = IW + 1;
+    constexpr int IW = TW + 2 * HALO, IH = TH + 2 * HALO, IP2 = IW + 1;
     constexpr int RPP = NT / IW;  // rows per pass
     const int x = tid % IW, y0 = tid / IW;
     if (y0 >= RPP) return;
@@ -80,57 +131,82 @@ __device__ __forceinline__ void load_tile(float* __restrict__ sIn, const float* 
         const int gy = ty0 - HALO + y;
         float v = 0.f;
         if (col_ok && gy >= 0 && gy < rows - 1) v = src8 ? (float)src8[(size_t)gy * pitch + gx] : __ldg(src + (size_t)gy * pitch + gx);
-        sIn[y * IP + x] = v;
+        sIn[il_index(y, x, IP2)] = v;
     }
 }
 
-// Masked tile load in two halves so that the global loads can be issued one tile ahead: tile_fetch (16-byte loads into
-// registers) and tile_stash (registers -> shared, applying the mask).  Needs a float4-aligned source: pitch % 4 == 0 and
-// tx0 % 32 == 0, so the window starts at tx0 - HALO - SLACK with SLACK = (-HALO) mod 4 extra columns dropped on the way in.
+// Masked tile load for a float source with even pitch and even tile origin, in two halves (global loads first, shared stores
+// after).  Warp w owns row pairs w, w+8, ...; lane l owns column pair l (a thread reads the same two columns of BOTH rows of a
+// pair: two 8-byte loads, coalesced along the row) -- so the column mask is computed once per thread, the row mask is warp
+// uniform and the addresses advance by a constant.  Tiles wider than 64 columns put the few extra column pairs in one more slot.
+// Every shared store writes complete float2 {row 2p, row 2p+1} entries: each store wavefront carries 128 useful bytes.
 // Mask = zero padding AND the reference's ">= rows-1 / cols-1 reads as zero" window fetch (src/sift.cpp:116).
 template <int HALO>
 struct TileIO {
-    static constexpr int SLACK = (4 - HALO % 4) % 4;
-    static constexpr int IW = TW + 2 * HALO, IH = TH + 2 * HALO, IP = IW + 1;
-    static constexpr int Q = (IW + 2 * SLACK) / 4;        // float4 per row
-    static constexpr int NSLOT = (IH * Q + NT - 1) / NT;  // float4 per thread
+    static_assert(HALO % 2 == 0, "8-byte aligned window");
+    static constexpr int IW = TW + 2 * HALO, IH = TH + 2 * HALO, IP2 = IW + 1;
+    static constexpr int Q = IW / 2, NP = IH / 2, NW = NT / 32;  // column pairs per row, row pairs, warps
+    static constexpr int NMAIN = (NP + NW - 1) / NW;              // main slots per thread
+    static constexpr int XC = Q > 32 ? Q - 32 : 0;                // extra column pairs
+    static constexpr int NX = (NP * XC + NT - 1) / NT;            // extra slots per thread
+    static constexpr int NSLOT = NMAIN + NX;
+    static_assert(NX <= 1, "one extra slot");
 
-    static __device__ __forceinline__ void fetch(float4 (&pre)[NSLOT], const float* __restrict__ src, int rows, int pitch, int ty0, int tx0, int tid) {
+    static __device__ __forceinline__ float2 ld_row(const float* p, bool ok) { return ok ? __ldg(reinterpret_cast<const float2*>(p)) : make_float2(0.f, 0.f); }
+
+    static __device__ __forceinline__ void fetch(float2 (&pre)[2 * NSLOT], const float* __restrict__ src, int rows, int pitch, int ty0, int tx0, int tid) {
+        const int lane = tid & 31, w = tid >> 5;
+        {
+            const int gx = tx0 - HALO + 2 * lane;
+            const bool col_ok = lane < Q && gx >= 0 && gx < pitch;
+            int gy = ty0 - HALO + 2 * w;
+            const float* ptr = src + (ptrdiff_t)gy * pitch + gx;
 #pragma unroll
-        for (int k = 0; k < NSLOT; ++k) {
-            const int idx = tid + k * NT;
-            const int y = idx / Q, q = idx - y * Q;
-            const int gy = ty0 - HALO + y, gx4 = tx0 - HALO - SLACK + 4 * q;
-            pre[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (idx < IH * Q && gy >= 0 && gy < rows - 1 && gx4 >= 0 && gx4 < pitch) pre[k] = __ldg(reinterpret_cast<const float4*>(src + (size_t)gy * pitch + gx4));
+            for (int k = 0; k < NMAIN; ++k) {
+                const bool pair_ok = col_ok && (w + NW * k < NP);
+                pre[2 * k] = ld_row(ptr, pair_ok && gy >= 0 && gy < rows - 1);
+                pre[2 * k + 1] = ld_row(ptr + pitch, pair_ok && gy + 1 >= 0 && gy + 1 < rows - 1);
+                gy += 2 * NW;
+                ptr += (ptrdiff_t)2 * NW * pitch;
+            }
+        }
+        if (NX) {
+            const int p = tid / (XC ? XC : 1), h = 32 + tid % (XC ? XC : 1);
+            const int gx = tx0 - HALO + 2 * h, gy = ty0 - HALO + 2 * p;
+            const bool ok = p < NP && gx >= 0 && gx < pitch;
+            const float* ptr = src + (ptrdiff_t)gy * pitch + gx;
+            pre[2 * NMAIN] = ld_row(ptr, ok && gy >= 0 && gy < rows - 1);
+            pre[2 * NMAIN + 1] = ld_row(ptr + pitch, ok && gy + 1 >= 0 && gy + 1 < rows - 1);
         }
     }
-    static __device__ __forceinline__ void stash(const float4 (&pre)[NSLOT], float* __restrict__ sIn, int cols, int tx0, int tid) {
+    static __device__ __forceinline__ void put(float2* out, float2 a, float2 b, int gx, int cols) {
+        out[0] = (gx >= 0 && gx < cols - 1) ? make_float2(a.x, b.x) : make_float2(0.f, 0.f);
+        out[1] = (gx + 1 >= 0 && gx + 1 < cols - 1) ? make_float2(a.y, b.y) : make_float2(0.f, 0.f);
+    }
+    static __device__ __forceinline__ void stash(const float2 (&pre)[2 * NSLOT], float2* __restrict__ sIn, int cols, int tx0, int tid) {
+        const int lane = tid & 31, w = tid >> 5;
+        if (lane < Q) {
+            const int gx = tx0 - HALO + 2 * lane;
 #pragma unroll
-        for (int k = 0; k < NSLOT; ++k) {
-            const int idx = tid + k * NT;
-            if (idx >= IH * Q) break;
-            const int y = idx / Q, q = idx - y * Q;
-            const int gx4 = tx0 - HALO - SLACK + 4 * q;
-            const float e[4] = {pre[k].x, pre[k].y, pre[k].z, pre[k].w};
-            float* out = sIn + y * IP + 4 * q - SLACK;
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                const int sx = 4 * q - SLACK + c, gx = gx4 + c;
-                if (sx >= 0 && sx < IW) out[c] = (gx >= 0 && gx < cols - 1) ? e[c] : 0.f;
-            }
+            for (int k = 0; k < NMAIN; ++k)
+                if (w + NW * k < NP) put(sIn + (w + NW * k) * IP2 + 2 * lane, pre[2 * k], pre[2 * k + 1], gx, cols);
+        }
+        if (NX) {
+            const int p = tid / (XC ? XC : 1), h = 32 + tid % (XC ? XC : 1);
+            if (p < NP) put(sIn + p * IP2 + 2 * h, pre[2 * NMAIN], pre[2 * NMAIN + 1], tx0 - HALO + 2 * h, cols);
         }
     }
 };
 
+// shared-memory offsets in float2 (one float2 = one column of a row pair)
 constexpr int H_OFF1 = 0;
-constexpr int H_OFF2 = H_OFF1 + (TH + 2 * 4) * HP;
-constexpr int H_OFF3 = H_OFF2 + (TH + 2 * 8) * HP;
-constexpr int H_OFF4 = H_OFF3 + (TH + 2 * 12) * HP;
-constexpr int H_END = H_OFF4 + (TH + 2 * 18) * HP;
+constexpr int H_OFF2 = H_OFF1 + (TH / 2 + 4) * HP2;
+constexpr int H_OFF3 = H_OFF2 + (TH / 2 + 8) * HP2;
+constexpr int H_OFF4 = H_OFF3 + (TH / 2 + 12) * HP2;
+constexpr int H_END = H_OFF4 + (TH / 2 + 18) * HP2;
 constexpr int OCT_HALO = kMaxRadius;
-constexpr int OCT_IN = (TW + 2 * OCT_HALO + 1) * (TH + 2 * OCT_HALO);
-constexpr int OCT_SMEM_BYTES = (OCT_IN + H_END) * 4;
+constexpr int OCT_IN = (TW + 2 * OCT_HALO + 1) * (TH / 2 + OCT_HALO);
+constexpr int OCT_SMEM_BYTES = (OCT_IN + H_END) * 8;
 
 struct OctArgs {
     const float* G0;
@@ -146,16 +222,16 @@ struct OctArgs {
 // kept the next tile's loads in flight in registers (128 registers -> 2 CTAs/SM, 46.7 us), and a CTA marching down four blocks
 // re-using the last 2R horizontal-pass rows (13 % fewer FFMAs but spills, an extra barrier and a row shift per block: 46 us).
 __global__ void __launch_bounds__(NT, 3) octave_kernel(const OctArgs a) {
-    extern __shared__ float smem[];
-    float* sIn = smem;
-    float* sH = smem + OCT_IN;
+    extern __shared__ float2 smem2[];
+    float2* sIn = smem2;
+    float2* sH = smem2 + OCT_IN;
     using IO = TileIO<OCT_HALO>;
     const int tid = threadIdx.x;
     const int tx0 = blockIdx.x * TW, ty0 = blockIdx.y * TH;
     const int f = blockIdx.z;
     const size_t foff = (size_t)f * a.frame_stride;
     {
-        float4 pre[IO::NSLOT];
+        float2 pre[2 * IO::NSLOT];
         IO::fetch(pre, a.G0 + foff, a.rows, a.pitch, ty0, tx0, tid);
         IO::stash(pre, sIn, a.cols, tx0, tid);
     }
@@ -168,21 +244,53 @@ __global__ void __launch_bounds__(NT, 3) octave_kernel(const OctArgs a) {
 
     const int x = tid & 31, rg = tid >> 5;
     float g1[GRP], g2[GRP], g3[GRP], g4[GRP];
-    fir8<1, HP>(sH + H_OFF1 + (rg * GRP) * HP + x, g1);
-    fir8<2, HP>(sH + H_OFF2 + (rg * GRP) * HP + x, g2);
-    fir8<3, HP>(sH + H_OFF3 + (rg * GRP) * HP + x, g3);
-    fir8<4, HP>(sH + H_OFF4 + (rg * GRP) * HP + x, g4);
+    fir8_col<1>(sH + H_OFF1 + (rg * GRP / 2) * HP2 + x, g1);
+    fir8_col<2>(sH + H_OFF2 + (rg * GRP / 2) * HP2 + x, g2);
+    fir8_col<3>(sH + H_OFF3 + (rg * GRP / 2) * HP2 + x, g3);
+    fir8_col<4>(sH + H_OFF4 + (rg * GRP / 2) * HP2 + x, g4);
 
     const int gx = tx0 + x;
-    constexpr int IP = TW + 2 * OCT_HALO + 1;
+    constexpr int IP2 = TW + 2 * OCT_HALO + 1;
+    const float* sInF = reinterpret_cast<const float*>(sIn);
+    const int r0 = rg * GRP;
+    if (ty0 + TH <= a.rows - 1 && tx0 + TW <= a.cols - 1) {
+        // interior tile (no pixel on the last row/column, none outside): no per-pixel checks.  Every level is addressed as
+        // (uniform 64-bit frame base) + (one 32-bit byte offset shared by all eight arrays), so a row costs one integer add.
+        char *const G1 = reinterpret_cast<char*>(a.G1 + foff), *const G2 = reinterpret_cast<char*>(a.G2 + foff);
+        char *const G3 = reinterpret_cast<char*>(a.G3 + foff), *const G4 = reinterpret_cast<char*>(a.G4 + foff);
+        char *const D0 = reinterpret_cast<char*>(a.D0 + foff), *const D1 = reinterpret_cast<char*>(a.D1 + foff);
+        char *const D2 = reinterpret_cast<char*>(a.D2 + foff), *const D3 = reinterpret_cast<char*>(a.D3 + foff);
+        char* const NX = reinterpret_cast<char*>(a.nextG0 + (size_t)f * a.nframe_stride);
+        const uint32_t pitch4 = (uint32_t)a.pitch * 4u, npitch4 = (uint32_t)a.npitch * 4u;
+        uint32_t off = (uint32_t)(ty0 + r0) * pitch4 + (uint32_t)gx * 4u;
+        uint32_t noff = (uint32_t)((ty0 + r0) >> 1) * npitch4 + (uint32_t)(gx >> 1) * 4u;
+        const bool deep = a.G3 != nullptr, next = a.nextG0 != nullptr && !(x & 1);
+        auto st = [](char* base, uint32_t o, float v) { *reinterpret_cast<float*>(base + o) = v; };
+#pragma unroll
+        for (int k = 0; k < GRP; ++k, off += pitch4) {
+            const float g0 = sInF[il_index(OCT_HALO + r0 + k, OCT_HALO + x, IP2)];
+            st(G1, off, g1[k]);
+            st(G2, off, g2[k]);
+            if (deep) { st(G3, off, g3[k]); st(G4, off, g4[k]); }
+            st(D0, off, g1[k] - g0);
+            st(D1, off, g2[k] - g1[k]);
+            st(D2, off, g3[k] - g2[k]);
+            st(D3, off, g4[k] - g3[k]);
+            if (!(k & 1)) {
+                if (next) st(NX, noff, g2[k]);
+                noff += npitch4;
+            }
+        }
+        return;
+    }
     if (gx >= a.cols) return;
 #pragma unroll
     for (int k = 0; k < GRP; ++k) {
-        const int gy = ty0 + rg * GRP + k;
+        const int gy = ty0 + r0 + k;
         if (gy >= a.rows) break;
         const size_t p = foff + (size_t)gy * a.pitch + gx;
         // DoG level 0 uses the real base value; the masked copy in shared memory is zero on the last row/col.
-        float g0 = sIn[(OCT_HALO + rg * GRP + k) * IP + OCT_HALO + x];
+        float g0 = sInF[il_index(OCT_HALO + r0 + k, OCT_HALO + x, IP2)];
         if (gy == a.rows - 1 || gx == a.cols - 1) g0 = __ldg(a.G0 + p);
         a.G1[p] = g1[k];
         a.G2[p] = g2[k];
@@ -200,24 +308,25 @@ __global__ void __launch_bounds__(NT, 3) octave_kernel(const OctArgs a) {
 
 // ---- base blur: image -> octave-0 base, sigma = sqrt(1.6^2 + 0.2^2), radius 4 (src/sift.cpp:237) ----------
 constexpr int BASE_HALO = 4;
-constexpr int BASE_IN = (TW + 2 * BASE_HALO + 1) * (TH + 2 * BASE_HALO);
-constexpr int BASE_SMEM_BYTES = (BASE_IN + (TH + 2 * 4) * HP) * 4;
+constexpr int BASE_IN = (TW + 2 * BASE_HALO + 1) * (TH / 2 + BASE_HALO);
+constexpr int BASE_SMEM_BYTES = (BASE_IN + (TH / 2 + 4) * HP2) * 8;
 
 __global__ void __launch_bounds__(NT, 4)
     base_blur_kernel(const float* __restrict__ src, const uint8_t* __restrict__ src8, size_t src_frame_stride, int src_pitch, float* __restrict__ dst,
                      size_t dst_frame_stride, int dst_pitch, int rows, int cols, int vec) {
-    extern __shared__ float smem[];
-    float* sIn = smem;
-    float* sH = smem + BASE_IN;
+    extern __shared__ float2 smem2[];
+    float2* sIn = smem2;
+    float2* sH = smem2 + BASE_IN;
+    float* sInF = reinterpret_cast<float*>(sIn);
     const int tid = threadIdx.x;
     const int tx0 = blockIdx.x * TW, ty0 = blockIdx.y * TH;
-    if (vec) {  // float source, 16-byte aligned rows: float4 loads
+    if (vec) {  // float source, aligned rows: 8-byte loads of row pairs
         using IO = TileIO<BASE_HALO>;
-        float4 pre[IO::NSLOT];
+        float2 pre[2 * IO::NSLOT];
         IO::fetch(pre, src + (size_t)blockIdx.z * src_frame_stride, rows, src_pitch, ty0, tx0, tid);
         IO::stash(pre, sIn, cols, tx0, tid);
     } else {
-        load_tile<BASE_HALO>(sIn, src ? src + (size_t)blockIdx.z * src_frame_stride : nullptr, src8 ? src8 + (size_t)blockIdx.z * src_frame_stride : nullptr,
+        load_tile<BASE_HALO>(sInF, src ? src + (size_t)blockIdx.z * src_frame_stride : nullptr, src8 ? src8 + (size_t)blockIdx.z * src_frame_stride : nullptr,
                              rows, cols, src_pitch, ty0, tx0, tid);
     }
     __syncthreads();
@@ -225,7 +334,7 @@ __global__ void __launch_bounds__(NT, 4)
     __syncthreads();
     const int x = tid & 31, rg = tid >> 5;
     float g[GRP];
-    fir8<0, HP>(sH + (rg * GRP) * HP + x, g);
+    fir8_col<0>(sH + (rg * GRP / 2) * HP2 + x, g);
     const int gx = tx0 + x;
     if (gx >= cols) return;
 #pragma unroll
