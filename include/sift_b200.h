@@ -102,6 +102,13 @@ int sift_b200_upsample2x_dev(SiftB200* h, const float* d_src, int n_frames, int 
 int sift_b200_detect_describe_up2(SiftB200* h, const float* img, int rows, int cols, SiftKeypoint* kp_out, float* desc_out, int cap,
                                   int* n_out, float* upsampled_out /* optional 2rows x 2cols host copy */);
 
+/* Exact-pyramid mode (off by default; env SIFT_B200_EXACT_PYRAMID=1 turns it on at create).  The default pyramid is the separable
+ * form of Gaussian_Blur, equal to the reference's non-separable loop (src/sift.cpp:110-153) up to float rounding.  With on != 0 every
+ * later call on this handle (whole path and build_gaussian_pyramid) replays that loop literally -- same 2-D taps, same row-major
+ * summation order, separately rounded multiply and add -- so the Gaussian/DoG pyramids are bit-identical to the reference's.  About
+ * 4x slower; meant for validation. */
+int sift_b200_set_exact_pyramid(SiftB200* h, int on);
+
 /* ---- sub-modules (include/sift.hpp:47-67), host buffers, synchronous ---------------------------- */
 
 /* Gaussian_Blur (include/sift.hpp:47, src/sift.cpp:123-153): unnormalised truncated 2-D Gaussian,

@@ -31,7 +31,7 @@ ABI_SYMBOLS = [
     "sift_b200_detect_describe", "sift_b200_detect_describe_batch_dev", "sift_b200_detect_describe_batch_host",
     "sift_b200_detect_describe_batch_host_u8", "sift_b200_detect_describe_batch_dev_u8", "sift_b200_rgb2gray_u8_dev", "sift_b200_upsample2x_dev", "sift_b200_detect_describe_up2", "sift_b200_gaussian_blur", "sift_b200_gaussian_blur_1d",
     "sift_b200_build_gaussian_pyramid", "sift_b200_build_dog_pyramid", "sift_b200_find_scale_space_extrema",
-    "sift_b200_cal_descriptor", "sift_b200_match_knn2", "sift_b200_match_knn2_ex", "sift_b200_launch_count", "sift_b200_set_stage_timing",
+    "sift_b200_cal_descriptor", "sift_b200_match_knn2", "sift_b200_match_knn2_ex", "sift_b200_set_exact_pyramid", "sift_b200_launch_count", "sift_b200_set_stage_timing",
     "sift_b200_get_stage_ms",
 ]
 
@@ -220,6 +220,10 @@ class Sift:
     # ---- introspection ----
     def launch_count(self) -> int:
         return int(lib().sift_b200_launch_count(self._h))
+
+    def set_exact_pyramid(self, on: bool):
+        """Replay the reference's non-separable Gaussian_Blur loop bit for bit (src/sift.cpp:110-153); ~4x slower, for validation."""
+        self._check(lib().sift_b200_set_exact_pyramid(self._h, int(on)))
 
     def set_stage_timing(self, on: bool):
         self._check(lib().sift_b200_set_stage_timing(self._h, int(on)))

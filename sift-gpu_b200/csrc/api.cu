@@ -52,6 +52,7 @@ struct SiftB200 {
     // second staging set + copy streams for the pipelined host-batch entry point
     float* d_img2 = nullptr;
     float* d_img3 = nullptr;  // third input buffer: lets the H2D copy run one chunk ahead of the two compute lanes
+    bool exact_pyramid = false;  // replay the reference's non-separable blur loop bit for bit (pyramid_exact.cu)
     bool taper = true;        // host batch: short chunks at both ends of a call (env SIFT_B200_TAPER=0 disables)
     SiftKeypoint* d_kp2 = nullptr;
     float* d_desc2 = nullptr;
@@ -123,6 +124,21 @@ int make_taps(float sigma, float* taps /* >= 2*radius+1 */, int max_radius) {
     const double norm = sqrt(1. / (2 * PI * sigma * sigma));
     for (int i = -w; i <= w; ++i) taps[i + w] = (float)(norm * exp(-(double)(i * i) / (double)den_f));
     return w;
+}
+
+// The reference's 2-D taps (src/sift.cpp:95-108): den = 2*sigma*sigma in FLOAT, the rest in double, x8192, rounded to float once.
+void make_taps_2d(float sigma, float* k /* (2w+1)^2, row-major */) {
+    const float t3 = 3 * sigma;
+    const int w = (int)floor((double)t3);
+    const int size = 2 * w + 1;
+    const float den_f = 2 * sigma * sigma;
+    const double PI = 3.14159265359;
+    for (int i = -w; i <= w; ++i)
+        for (int j = -w; j <= w; ++j) {
+            double dat = 1. / (2 * PI * sigma * sigma) * exp(-(i * i + j * j) * 1. / (double)den_f);
+            dat = dat * 8192;
+            k[(i + w) * size + (j + w)] = (float)dat;
+        }
 }
 
 void pipeline_sigmas(float sig[5]) {
@@ -210,9 +226,9 @@ int enqueue_chunk(SiftB200* h, int lane, const float* d_imgs, const uint8_t* d_i
     const DetectBuf& db = lane ? h->db2 : h->db;
     const size_t fs = (size_t)rows * cols;
     if (timing) cudaEventRecord(h->ev[0], st);
-    h->launches += launch_base_blur(d_imgs, fs, cols, d_imgs8, pv.oct[0], nf, st);
+    h->launches += h->exact_pyramid ? launch_exact_base(d_imgs, fs, cols, d_imgs8, pv.oct[0], nf, st) : launch_base_blur(d_imgs, fs, cols, d_imgs8, pv.oct[0], nf, st);
     if (timing) cudaEventRecord(h->ev[1], st);
-    for (int o = 0; o < n_oct; ++o) h->launches += launch_octave(pv, o, nf, false, st);
+    for (int o = 0; o < n_oct; ++o) h->launches += h->exact_pyramid ? launch_exact_octave(pv, o, nf, false, st) : launch_octave(pv, o, nf, false, st);
     if (timing) cudaEventRecord(h->ev[2], st);
     h->launches += launch_gradient(pv, nf, st);
     if (timing) cudaEventRecord(h->ev[3], st);
@@ -294,6 +310,7 @@ int sift_b200_create(SiftB200** out, int max_rows, int max_cols, int max_batch, 
     if (int rc_db = alloc_detectbuf(h->db, F, max_kp_per_frame)) return rc_db;
     if (const char* e = getenv("SIFT_B200_LANES")) h->lanes = atoi(e);
     if (const char* e = getenv("SIFT_B200_TAPER")) h->taper = atoi(e) != 0;
+    if (const char* e = getenv("SIFT_B200_EXACT_PYRAMID")) h->exact_pyramid = atoi(e) != 0;
     CUDA_TRY(cudaMalloc((void**)&h->d_counts, F * sizeof(int)));
     CUDA_TRY(cudaMallocHost((void**)&h->h_counts, F * sizeof(int)));
     for (auto& e : h->ev) CUDA_TRY(cudaEventCreate(&e));
@@ -304,6 +321,11 @@ int sift_b200_create(SiftB200** out, int max_rows, int max_cols, int max_batch, 
     for (int s = 0; s < 5; ++s)
         if (make_taps(sig[s], taps[s], kMaxRadius) < 0) return fail(SIFT_B200_ERR_ARG, "tap radius");
     upload_taps(taps);
+    {
+        std::vector<float> k2d(k2d_total());
+        for (int s = 0; s < 5; ++s) make_taps_2d(sig[s], k2d.data() + k2d_offset(s));
+        upload_taps_2d(k2d.data());
+    }
     init_pyramid_kernels();
     init_detect_kernels();
     init_describe_kernels();
@@ -608,8 +630,13 @@ int sift_b200_build_gaussian_pyramid(SiftB200* h, const float* img, int rows, in
     PyrView pv;
     if ((rc = make_view(h->ws_full, rows, cols, n_octaves, 1, true, &pv))) return fail(rc, "make_view");
     CUDA_TRY(cudaMemcpyAsync(h->d_img, img, (size_t)rows * cols * 4, cudaMemcpyHostToDevice, h->stream));
-    h->launches += launch_base_blur(h->d_img, (size_t)rows * cols, cols, nullptr, pv.oct[0], 1, h->stream);
-    for (int o = 0; o < n_octaves; ++o) h->launches += launch_octave(pv, o, 1, true, h->stream);
+    if (h->exact_pyramid) {
+        h->launches += launch_exact_base(h->d_img, (size_t)rows * cols, cols, nullptr, pv.oct[0], 1, h->stream);
+        for (int o = 0; o < n_octaves; ++o) h->launches += launch_exact_octave(pv, o, 1, true, h->stream);
+    } else {
+        h->launches += launch_base_blur(h->d_img, (size_t)rows * cols, cols, nullptr, pv.oct[0], 1, h->stream);
+        for (int o = 0; o < n_octaves; ++o) h->launches += launch_octave(pv, o, 1, true, h->stream);
+    }
     if ((rc = copy_levels(pv, true, 5, gpyr, false, h->stream))) return rc;
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     CUDA_TRY(cudaGetLastError());
@@ -728,6 +755,12 @@ int sift_b200_match_knn2(SiftB200* h, const float* query, int nq, const float* t
 }
 
 long long sift_b200_launch_count(const SiftB200* h) { return h ? h->launches : 0; }
+
+int sift_b200_set_exact_pyramid(SiftB200* h, int on) {
+    if (!h) return fail(SIFT_B200_ERR_ARG, "null handle");
+    h->exact_pyramid = on != 0;
+    return SIFT_B200_OK;
+}
 
 int sift_b200_set_stage_timing(SiftB200* h, int on) {
     if (!h) return fail(SIFT_B200_ERR_ARG, "null handle");

@@ -80,6 +80,12 @@ void init_match_tc_kernels();
 int launch_base_blur(const float* src, size_t src_frame_stride, int src_pitch, const uint8_t* src_u8, const OctaveView& o0, int n_frames,
                      cudaStream_t st);
 int launch_octave(const PyrView& pv, int o, int n_frames, bool write_all_levels, cudaStream_t st);
+// exact-order pyramid (pyramid_exact.cu): same outputs as the two launchers above, bit-identical to the reference's loop
+void upload_taps_2d(const float* host_k2d);
+int k2d_total();
+int k2d_offset(int s);
+int launch_exact_base(const float* src, size_t src_frame_stride, int src_pitch, const uint8_t* src_u8, const OctaveView& o0, int n_frames, cudaStream_t st);
+int launch_exact_octave(const PyrView& pv, int o, int n_frames, bool write_all_levels, cudaStream_t st);
 int launch_generic_blur(const float* src, float* dst, int rows, int cols, const float* d_taps, int radius, int taps_hi, cudaStream_t st);
 int launch_dog(const PyrView& pv, int n_frames, cudaStream_t st);
 int launch_rgb2gray_u8(const uint8_t* src, uint8_t* dst, size_t n_pixels, cudaStream_t st);
