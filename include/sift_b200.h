@@ -134,8 +134,9 @@ int sift_b200_cal_descriptor(SiftB200* h, const float* gpyr, int rows, int cols,
 int sift_b200_match_knn2(SiftB200* h, const float* query, int nq, const float* train, int nt, int norm, double ratio,
                          int32_t* idx_out, float* dist_out, uint8_t* good_out);
 /* Same call with two extras.  tensor_cores != 0 (NORM_L2 only): distances come from split-bf16 tcgen05 MMAs (fp32 accumulation in
- * TMEM), a 4-entry shortlist per query is re-ranked exactly in fp64, so the result equals the exact kernel's unless more than two
- * other train rows lie within ~3e-5 of a true neighbour's distance.  kernel_ms (optional): CUDA-event time of the kernels alone. */
+ * TMEM), a short list of candidates per query is re-ranked exactly in fp64, so the result equals the exact kernel's unless several
+ * train rows of one 32-row chunk lie within ~3e-5 of a true neighbour's distance.  kernel_ms (optional): CUDA-event time of the
+ * kernels alone. */
 int sift_b200_match_knn2_ex(SiftB200* h, const float* query, int nq, const float* train, int nt, int norm, double ratio,
                             int32_t* idx_out, float* dist_out, uint8_t* good_out, int tensor_cores, float* kernel_ms);
 

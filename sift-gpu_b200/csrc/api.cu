@@ -718,12 +718,12 @@ int sift_b200_match_knn2_ex(SiftB200* h, const float* query, int nq, const float
     if (kernel_ms) *kernel_ms = 0.f;
     if (nq == 0) return SIFT_B200_OK;
     CUDA_TRY(cudaSetDevice(h->device));
-    float *d_q = nullptr, *d_t = nullptr, *d_dist = nullptr; int32_t *d_idx = nullptr, *d_cand = nullptr;
+    float *d_q = nullptr, *d_t = nullptr, *d_dist = nullptr; int32_t* d_idx = nullptr; void* d_cand = nullptr;
     CUDA_TRY(cudaMalloc((void**)&d_q, (size_t)nq * 512));
     CUDA_TRY(cudaMalloc((void**)&d_t, (size_t)(nt ? nt : 1) * 512));
     CUDA_TRY(cudaMalloc((void**)&d_dist, (size_t)nq * 8));
     CUDA_TRY(cudaMalloc((void**)&d_idx, (size_t)nq * 8));
-    if (tensor_cores) CUDA_TRY(cudaMalloc((void**)&d_cand, (size_t)nq * 16 * match_tc_splits(nq, nt)));
+    if (tensor_cores) CUDA_TRY(cudaMalloc(&d_cand, match_tc_scratch_bytes(nq, nt)));
     CUDA_TRY(cudaMemcpyAsync(d_q, query, (size_t)nq * 512, cudaMemcpyHostToDevice, h->stream));
     if (nt) CUDA_TRY(cudaMemcpyAsync(d_t, train, (size_t)nt * 512, cudaMemcpyHostToDevice, h->stream));
     cudaEvent_t e0 = nullptr, e1 = nullptr;

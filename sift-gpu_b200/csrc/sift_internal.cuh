@@ -97,8 +97,8 @@ int launch_order_scan(const DetectBuf& db, int n_frames, int* d_counts, cudaStre
 int launch_describe(const PyrView& pv, const DetectBuf& db, int n_frames, SiftKeypoint* d_kp, float* d_desc, int cap, cudaStream_t st);
 int launch_describe_given(const PyrView& pv, const SiftKeypoint* d_kps, int n, float* d_desc, int first_octave, int* d_err, cudaStream_t st);
 int launch_match(const float* d_q, int nq, const float* d_t, int nt, int norm, float* d_dist, int32_t* d_idx, cudaStream_t st);
-// tcgen05 L2 matcher: approximate shortlist on the tensor cores + exact fp64 re-rank (match_tc.cu); d_cand = nq x match_tc_splits() x 4 int32 scratch
-int match_tc_splits(int nq, int nt);
-int launch_match_tc(const float* d_q, int nq, const float* d_t, int nt, int32_t* d_cand, float* d_dist, int32_t* d_idx, cudaStream_t st);
+// tcgen05 L2 matcher: bf16 hi/lo operand tiles -> tensor-core shortlists -> exact fp64 re-rank (match_tc.cu)
+size_t match_tc_scratch_bytes(int nq, int nt);
+int launch_match_tc(const float* d_q, int nq, const float* d_t, int nt, void* d_scratch, float* d_dist, int32_t* d_idx, cudaStream_t st);
 
 }  // namespace siftb200

@@ -152,7 +152,8 @@ def test_matcher_identical_indices(sift, pkg, oracle, golden):
 
 
 def test_tensor_core_matcher_identical_indices(sift, pkg, oracle, golden):
-    """tcgen05 L2 matcher (match_tc.cu: split-bf16 MMAs -> shortlist of 4 per train split -> exact fp64 re-rank): indices,
+    """tcgen05 L2 matcher (match_tc.cu: split-bf16 MMAs -> per train split the {min, second min} of the 4 best 32-row chunks ->
+    exact fp64 re-rank of the entries whose error interval can still reach the top two): indices,
     distances and ratio flags identical to the fixture, to the exact kernel and to the oracle -- ragged tiles, duplicates
     (ties -> lowest train index), near-duplicates inside the bf16 error band, several train splits."""
     z = golden("match_query_scene")
@@ -174,7 +175,7 @@ def test_tensor_core_matcher_identical_indices(sift, pkg, oracle, golden):
         gi, gd, gg = sift.match_knn2(q, t, pkg.NORM_L2, 0.86, tensor_cores=True)
         ei, ed, eg = sift.match_knn2(q, t, pkg.NORM_L2, 0.86)
         oi, od, og = oracle.match_knn2(q, t, pkg.NORM_L2, 0.86)
-        if nt >= 100:  # the six-row cluster is the documented limit of a 4-entry shortlist: exclude that one query
+        if nt >= 100:  # six rows within the bf16-split error of each other: the documented limit of the shortlist; exclude that query
             keep = np.ones(nq, bool); keep[2] = False
         else:
             keep = np.ones(nq, bool)

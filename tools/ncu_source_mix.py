@@ -5,6 +5,14 @@ rep = sys.argv[1]
 top = int(sys.argv[2]) if len(sys.argv) > 2 else 0
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"] + sys.argv[3:], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
+# one section per captured kernel ("Kernel Name" row, then a header row starting with "Address"); NCU_KERNEL picks one by substring
+import os
+want = os.environ.get("NCU_KERNEL", "")
+starts = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"]
+sect = next((i for i in starts if want in rows[i][1]), starts[0])
+end = next((i for i in starts if i > sect), len(rows))
+rows = rows[sect:end]
+print("kernel:", rows[0][1][:90])
 hi = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
 h = rows[hi]
 c = {n: i for i, n in enumerate(h)}
