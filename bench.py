@@ -222,6 +222,28 @@ def run_reference(args, out):
 
 
 # ---- our arm --------------------------------------------------------------------------------------------------
+def bind_near_gpu(index: int):
+    """Pin this process to the CPUs NVML reports as local to GPU `index`, so that the pinned host buffers allocated afterwards
+    (first touch) sit on the GPU's own NUMA node -- with 8 ranks on a two-socket box, remote buffers halve the host<->device rate.
+    Returns (previous affinity, number of CPUs bound to) or (None, 0) when NVML or the affinity call is unavailable."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1}
+        prev = os.sched_getaffinity(0)
+        cpus &= prev
+        if not cpus:
+            return None, 0
+        os.sched_setaffinity(0, cpus)
+        return prev, len(cpus)
+    except Exception:
+        return None, 0
+
+
 def run_ours(args, out):
     import torch
     import torch.distributed as dist
@@ -231,6 +253,7 @@ def run_ours(args, out):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- this framework has no CPU fallback")
+    prev_affinity, numa_cpus = bind_near_gpu(local_rank)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -358,7 +381,36 @@ def run_ours(args, out):
               "api": "sift_b200_detect_describe_batch_host_u8 (frames rounded to uint8: a different input than the float frames above)"}
     clocks = sampler.stop(windows) if sampler else None
 
+    # side measurements (rank 0, N=1): not part of `value`.  (1) the same frames with the opt-in exact-pyramid mode, i.e. the
+    # reference's own blur summation order; (2) the driver's matcher on its own workload size (src/main.cpp:25-40
+    # on data/query.jpg vs data/scene.jpg: 1358 x 1444 descriptors), exact kernel vs tensor-core path, CUDA-event kernel time.
+    extras = {}
+    if rank == 0 and world == 1:
+        nx = min(B, 2 * chunk)
+        s.set_exact_pyramid(True)
+        s.detect_describe_batch_dev(d_imgs[:nx], d_kp[:nx], d_desc[:nx], d_cnt[:nx], cap, st)
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        s.detect_describe_batch_dev(d_imgs[:nx], d_kp[:nx], d_desc[:nx], d_cnt[:nx], cap, st)
+        torch.cuda.synchronize(dev)
+        extras["exact_pyramid"] = {"value": nx / (time.perf_counter() - t0), "unit": "frames/s",
+                                   "note": "pyramid bit-identical to the reference (non-separable loop replayed); validation mode"}
+        s.set_exact_pyramid(False)
+        rng = np.random.default_rng(5)
+        qd = np.sqrt(rng.dirichlet(np.full(128, 0.6), 1358)).astype(np.float32)
+        td = np.sqrt(rng.dirichlet(np.full(128, 0.6), 1444)).astype(np.float32)
+        ms_tc, ms_ex, same = [], [], True
+        for _ in range(4):
+            i1, d1, g1, m1 = s.match_knn2(qd, td, pkg.NORM_L2, 0.86, tensor_cores=True, timing=True)
+            i0, d0, g0, m0 = s.match_knn2(qd, td, pkg.NORM_L2, 0.86, timing=True)
+            ms_tc.append(m1); ms_ex.append(m0)
+            same = same and bool(np.array_equal(i0, i1) and np.array_equal(d0, d1))
+        extras["matcher"] = {"workload": "1358 x 1444 RootSIFT-like descriptors, NORM_L2, knn 2 + ratio 0.86", "tensor_core_us": round(min(ms_tc) * 1e3, 1),
+                             "exact_fp64_us": round(min(ms_ex) * 1e3, 1), "identical_indices_and_distances": same}
+
     cpu_base = None
+    if prev_affinity is not None:
+        os.sched_setaffinity(0, prev_affinity)  # the CPU baseline below uses every host core
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu_base, _ = cpu_reference_run(1, 0, budget_s=22.0)
     if rank == 0:
@@ -366,9 +418,11 @@ def run_ours(args, out):
                 "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": WORKLOAD, "frames_per_step_per_gpu": B, "chunk_frames": chunk, "keypoint_capacity": cap,
                            "mean_keypoints_per_frame": round(n_kp, 1), "parallelism": f"frame-sharded x{world}, no collectives",
-                           "l2": f"inputs larger than L2: {B} frames x 8.3 MB per step, workspace {chunk} x 77 MB"},
+                           "l2": f"inputs larger than L2: {B} frames x 8.3 MB per step, workspace {chunk} x 77 MB",
+                           "host_cpus_bound_to_gpu_numa_node": numa_cpus},
                 "e2e": e2e, "e2e_u8": e2e_u8, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "roofline_by_kernel": by_kernel,
                 "roofline_pipeline": roofline_pipeline, "cpu_baseline": cpu_base}
+        line.update(extras)
         out.emit(json.dumps(line))
     s.close()
     if world > 1:
