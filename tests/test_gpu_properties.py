@@ -89,6 +89,40 @@ def test_batch_dev_equals_single_frames(pkg, synth):
     s.close()
 
 
+def test_host_batch_tapered_schedule(pkg, synth):
+    """The host batch pipeline (three input buffers, two compute lanes, short chunks at both ends of a call: api.cu chunk_plan)
+    returns for every frame exactly what the device-resident call returns: 13 frames with max_batch 4 -> chunks 1,2,3,4,2,1;
+    6 frames (below the taper threshold) -> 2,4; and a capacity overflow in one frame is reported without disturbing the others."""
+    import torch
+
+    n = 13
+    frames = np.stack([synth.recipe_s(320, 200, seed=300 + k) for k in range(n)])
+    cap = 2048
+    s = pkg.Sift(200, 320, max_batch=4, max_kp_per_frame=cap)
+    d = torch.from_numpy(frames).cuda()
+    d_kp = torch.zeros((n, cap, 28), dtype=torch.uint8, device="cuda")
+    d_desc = torch.zeros((n, cap, 128), dtype=torch.float32, device="cuda")
+    d_cnt = torch.zeros(n, dtype=torch.int32, device="cuda")
+    s.detect_describe_batch_dev(d, d_kp, d_desc, d_cnt, cap, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    cnt = d_cnt.cpu().numpy()
+    assert cnt.min() > 20
+    for m in (n, 6, 1):
+        h_kp = np.zeros((m, cap), dtype=pkg.KP_DTYPE); h_desc = np.zeros((m, cap, 128), dtype=np.float32); h_cnt = np.zeros(m, dtype=np.int32)
+        assert s.detect_describe_batch_host(frames[:m], h_kp, h_desc, h_cnt, cap) == pkg.OK
+        assert np.array_equal(h_cnt, cnt[:m])
+        for f in range(m):
+            assert h_kp[f, : cnt[f]].tobytes() == d_kp[f, : cnt[f]].cpu().numpy().tobytes()
+            assert np.array_equal(h_desc[f, : cnt[f]], d_desc[f, : cnt[f]].cpu().numpy())
+    small = int(cnt.min()) - 1  # at least one frame overflows this capacity
+    h_kp = np.zeros((n, small), dtype=pkg.KP_DTYPE); h_desc = np.zeros((n, small, 128), dtype=np.float32); h_cnt = np.zeros(n, dtype=np.int32)
+    assert s.detect_describe_batch_host(frames, h_kp, h_desc, h_cnt, small) == pkg.ERR_CAPACITY
+    assert np.array_equal(h_cnt, cnt)  # true counts
+    for f in range(n):
+        assert np.array_equal(h_desc[f], d_desc[f, :small].cpu().numpy())  # the first `small` keypoints of every frame
+    s.close()
+
+
 def test_edge_cases_and_errors(pkg, oracle, synth):
     s = pkg.Sift(256, 256, max_batch=1, max_kp_per_frame=2048)
     # smallest image the reference admits (16 px: octave 4 is 1x1) -> no keypoints, like the oracle
