@@ -1,0 +1,53 @@
+"""Randomised-size parity sweep on the GPU: image shapes that put the tile / strip / halo boundaries of every kernel in odd places
+(widths not a multiple of 32, heights not a multiple of 64 or 16, the last row or column exactly on a tile edge, tiny octaves).
+Each case: whole path vs the oracle (reference src/sift.cpp:59-91 restated), and the exact-pyramid mode vs the oracle's pyramid
+bit for bit.  Run with -m gpu on a B200; the oracle needs well under a second per case."""
+import numpy as np
+import pytest
+
+import parity
+
+pytestmark = pytest.mark.gpu
+
+# hand-picked edge shapes + seeded random ones (rows, cols)
+EDGE = [(65, 33), (64, 32), (129, 97), (63, 31), (17, 400), (400, 17), (100, 68), (193, 257), (66, 34), (128, 160)]
+
+
+def _shapes():
+    rng = np.random.default_rng(20261018)
+    rnd = [(int(rng.integers(20, 420)), int(rng.integers(20, 520))) for _ in range(26)]
+    big = [(int(rng.integers(600, 1100)), int(rng.integers(700, 1400))) for _ in range(4)]
+    return EDGE + rnd + big
+
+
+@pytest.mark.parametrize("shape", _shapes(), ids=lambda s: f"{s[0]}x{s[1]}")
+def test_random_shapes_vs_oracle(sift, oracle, synth, shape):
+    rows, cols = shape
+    img = synth.recipe_s(cols, rows, seed=rows * 1000 + cols, blobs_per_1080p=30000)
+    assert img.shape == (rows, cols)
+    okp, odesc = oracle.f32().sift_ncl(img)[:2]
+    kp, desc = sift.detect_describe(img)
+    # separable pyramid: threshold-borderline points may flip (north star), so counts may differ by a few
+    pairs = parity.match_keypoints(kp, okp)
+    rec, prec = parity.recall_precision(pairs, len(kp), len(okp))
+    if len(okp) >= 100:
+        assert rec >= 0.99 and prec >= 0.99, (shape, len(kp), len(okp), rec, prec)
+    else:
+        assert abs(len(kp) - len(okp)) <= 1 and len(pairs) >= min(len(kp), len(okp)) - 1, (shape, len(kp), len(okp))
+    # exact-pyramid mode: identical pyramid -> identical keypoint records (angle to 1e-3 deg) and descriptors within 1e-3 (one flip allowed)
+    sift.set_exact_pyramid(True)
+    try:
+        g = sift.build_gaussian_pyramid(img, 5)
+        assert np.array_equal(g, oracle.f32().build_gaussian_pyramid(img, 5)), shape
+        kp, desc = sift.detect_describe(img)
+    finally:
+        sift.set_exact_pyramid(False)
+    assert len(kp) == len(okp), (shape, len(kp), len(okp))
+    if len(kp):
+        for fld in ("x", "y", "response", "octave"):
+            assert np.array_equal(kp[fld], okp[fld]), (shape, fld)
+        assert np.allclose(kp["size"], okp["size"], rtol=2.5e-7, atol=0), shape  # 1 ulp: exp2f here, powf in the reference (:384)
+        da = np.abs(kp["angle"] - okp["angle"])
+        assert np.minimum(da, 360 - da).max() <= 1e-3, shape
+        err = np.linalg.norm(desc - odesc, axis=1)
+        assert (err > 1e-3).sum() <= max(1, len(kp) // 200), (shape, float(err.max()))
