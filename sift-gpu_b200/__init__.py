@@ -31,7 +31,7 @@ ABI_SYMBOLS = [
     "sift_b200_detect_describe", "sift_b200_detect_describe_batch_dev", "sift_b200_detect_describe_batch_host",
     "sift_b200_detect_describe_batch_host_u8", "sift_b200_detect_describe_batch_dev_u8", "sift_b200_rgb2gray_u8_dev", "sift_b200_upsample2x_dev", "sift_b200_detect_describe_up2", "sift_b200_gaussian_blur", "sift_b200_gaussian_blur_1d",
     "sift_b200_build_gaussian_pyramid", "sift_b200_build_dog_pyramid", "sift_b200_find_scale_space_extrema",
-    "sift_b200_cal_descriptor", "sift_b200_match_knn2", "sift_b200_match_knn2_ex", "sift_b200_set_exact_pyramid", "sift_b200_launch_count", "sift_b200_set_stage_timing",
+    "sift_b200_cal_descriptor", "sift_b200_match_knn2", "sift_b200_match_knn2_ex", "sift_b200_match_knn2_dev", "sift_b200_set_exact_pyramid", "sift_b200_launch_count", "sift_b200_set_stage_timing",
     "sift_b200_get_stage_ms",
 ]
 
@@ -216,6 +216,12 @@ class Sift:
         if timing:
             return idx, dist, good.astype(bool), float(ms.value)
         return idx, dist, good.astype(bool)
+
+    def match_knn2_dev(self, d_query, d_train, d_idx, d_dist, norm: int = NORM_L1, tensor_cores: bool = False, stream: int = 0):
+        """Device-resident matcher: torch CUDA tensors [nq,128] / [nt,128] float32 in, [nq,2] int32 / float32 out, asynchronous."""
+        self._check(lib().sift_b200_match_knn2_dev(self._h, C.c_void_p(d_query.data_ptr()), d_query.shape[0], C.c_void_p(d_train.data_ptr()),
+                                                   d_train.shape[0], norm, C.c_void_p(d_idx.data_ptr()), C.c_void_p(d_dist.data_ptr()),
+                                                   int(tensor_cores), C.c_void_p(stream)))
 
     # ---- introspection ----
     def launch_count(self) -> int:

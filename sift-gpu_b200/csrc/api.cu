@@ -288,6 +288,20 @@ int run_pipeline(SiftB200* h, const float* d_imgs, const uint8_t* d_imgs8, int n
 
 }  // namespace
 
+namespace {
+// frees on every exit path of the synchronous entry points below
+struct DevMem {
+    void* p = nullptr;
+    ~DevMem() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1); }
+    template <class T> T* as() const { return static_cast<T*>(p); }
+};
+struct Event {
+    cudaEvent_t e = nullptr;
+    ~Event() { if (e) cudaEventDestroy(e); }
+};
+}  // namespace
+
 extern "C" {
 
 const char* sift_b200_last_error(void) { return g_err.c_str(); }
@@ -710,6 +724,27 @@ int sift_b200_cal_descriptor(SiftB200* h, const float* gpyr, int rows, int cols,
     return SIFT_B200_OK;
 }
 
+int sift_b200_match_knn2_dev(SiftB200* h, const float* d_query, int nq, const float* d_train, int nt, int norm, int32_t* d_idx, float* d_dist,
+                             int tensor_cores, void* stream) {
+    if (!h || nq < 0 || nt < 0 || (nq > 0 && (!d_query || !d_idx || !d_dist)) || (nt > 0 && !d_train)) return fail(SIFT_B200_ERR_ARG, "bad argument");
+    if (norm != SIFT_B200_NORM_L1 && norm != SIFT_B200_NORM_L2) return fail(SIFT_B200_ERR_ARG, "norm must be NORM_L1 (2) or NORM_L2 (4)");
+    if (tensor_cores && norm != SIFT_B200_NORM_L2) return fail(SIFT_B200_ERR_ARG, "the tensor-core matcher computes NORM_L2 only");
+    if (nq == 0) return SIFT_B200_OK;
+    CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    // a train set shorter than the shortlist goes through the exact kernel (its -1 / +inf padding rule)
+    if (tensor_cores && nt >= 4) {
+        void* scratch = nullptr;
+        CUDA_TRY(cudaMallocAsync(&scratch, match_tc_scratch_bytes(nq, nt), st));
+        h->launches += launch_match_tc(d_query, nq, d_train, nt, scratch, d_dist, d_idx, st);
+        CUDA_TRY(cudaFreeAsync(scratch, st));
+    } else {
+        h->launches += launch_match(d_query, nq, d_train, nt, norm, d_dist, d_idx, st);
+    }
+    CUDA_TRY(cudaGetLastError());
+    return SIFT_B200_OK;
+}
+
 int sift_b200_match_knn2_ex(SiftB200* h, const float* query, int nq, const float* train, int nt, int norm, double ratio, int32_t* idx_out,
                             float* dist_out, uint8_t* good_out, int tensor_cores, float* kernel_ms) {
     if (!h || nq < 0 || nt < 0 || (nq > 0 && (!query || !idx_out || !dist_out)) || (nt > 0 && !train)) return fail(SIFT_B200_ERR_ARG, "bad argument");
@@ -718,31 +753,25 @@ int sift_b200_match_knn2_ex(SiftB200* h, const float* query, int nq, const float
     if (kernel_ms) *kernel_ms = 0.f;
     if (nq == 0) return SIFT_B200_OK;
     CUDA_TRY(cudaSetDevice(h->device));
-    float *d_q = nullptr, *d_t = nullptr, *d_dist = nullptr; int32_t* d_idx = nullptr; void* d_cand = nullptr;
-    CUDA_TRY(cudaMalloc((void**)&d_q, (size_t)nq * 512));
-    CUDA_TRY(cudaMalloc((void**)&d_t, (size_t)(nt ? nt : 1) * 512));
-    CUDA_TRY(cudaMalloc((void**)&d_dist, (size_t)nq * 8));
-    CUDA_TRY(cudaMalloc((void**)&d_idx, (size_t)nq * 8));
-    if (tensor_cores) CUDA_TRY(cudaMalloc(&d_cand, match_tc_scratch_bytes(nq, nt)));
-    CUDA_TRY(cudaMemcpyAsync(d_q, query, (size_t)nq * 512, cudaMemcpyHostToDevice, h->stream));
-    if (nt) CUDA_TRY(cudaMemcpyAsync(d_t, train, (size_t)nt * 512, cudaMemcpyHostToDevice, h->stream));
-    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    DevMem q, t, dist, idx;
+    CUDA_TRY(q.alloc((size_t)nq * 512));
+    CUDA_TRY(t.alloc((size_t)nt * 512));
+    CUDA_TRY(dist.alloc((size_t)nq * 8));
+    CUDA_TRY(idx.alloc((size_t)nq * 8));
+    CUDA_TRY(cudaMemcpyAsync(q.p, query, (size_t)nq * 512, cudaMemcpyHostToDevice, h->stream));
+    if (nt) CUDA_TRY(cudaMemcpyAsync(t.p, train, (size_t)nt * 512, cudaMemcpyHostToDevice, h->stream));
+    Event e0, e1;
     if (kernel_ms) {
-        CUDA_TRY(cudaEventCreate(&e0)); CUDA_TRY(cudaEventCreate(&e1));
-        CUDA_TRY(cudaEventRecord(e0, h->stream));
+        CUDA_TRY(cudaEventCreate(&e0.e)); CUDA_TRY(cudaEventCreate(&e1.e));
+        CUDA_TRY(cudaEventRecord(e0.e, h->stream));
     }
-    // a train set shorter than the shortlist still goes through the exact kernel (its -1 / +inf padding rule)
-    if (tensor_cores && nt >= 4) h->launches += launch_match_tc(d_q, nq, d_t, nt, d_cand, d_dist, d_idx, h->stream);
-    else h->launches += launch_match(d_q, nq, d_t, nt, norm, d_dist, d_idx, h->stream);
-    if (kernel_ms) CUDA_TRY(cudaEventRecord(e1, h->stream));
-    CUDA_TRY(cudaMemcpyAsync(dist_out, d_dist, (size_t)nq * 8, cudaMemcpyDeviceToHost, h->stream));
-    CUDA_TRY(cudaMemcpyAsync(idx_out, d_idx, (size_t)nq * 8, cudaMemcpyDeviceToHost, h->stream));
-    cudaError_t sync_err = cudaStreamSynchronize(h->stream);
-    if (kernel_ms && sync_err == cudaSuccess) cudaEventElapsedTime(kernel_ms, e0, e1);
-    if (e0) cudaEventDestroy(e0);
-    if (e1) cudaEventDestroy(e1);
-    cudaFree(d_q); cudaFree(d_t); cudaFree(d_dist); cudaFree(d_idx); cudaFree(d_cand);
-    CUDA_TRY(sync_err);
+    const int rc = sift_b200_match_knn2_dev(h, q.as<float>(), nq, t.as<float>(), nt, norm, idx.as<int32_t>(), dist.as<float>(), tensor_cores, h->stream);
+    if (rc) return rc;
+    if (kernel_ms) CUDA_TRY(cudaEventRecord(e1.e, h->stream));
+    CUDA_TRY(cudaMemcpyAsync(dist_out, dist.p, (size_t)nq * 8, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaMemcpyAsync(idx_out, idx.p, (size_t)nq * 8, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    if (kernel_ms) CUDA_TRY(cudaEventElapsedTime(kernel_ms, e0.e, e1.e));
     CUDA_TRY(cudaGetLastError());
     if (good_out)  // ratio test exactly as written in the driver: float distance vs double product (src/main.cpp:38)
         for (int i = 0; i < nq; ++i) good_out[i] = (idx_out[2 * i + 1] >= 0 && dist_out[2 * i] <= ratio * dist_out[2 * i + 1]) ? 1 : 0;

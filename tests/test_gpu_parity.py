@@ -238,3 +238,31 @@ def test_exact_pyramid_mode_is_bit_identical(sift, pkg, oracle, golden):
         assert (err <= 1e-3).mean() >= 0.995, float((err <= 1e-3).mean())
     finally:
         sift.set_exact_pyramid(False)
+
+
+def test_config5_device_resident(sift, pkg, golden):
+    """Config 5 without leaving the device: query and scene through the batch entry point, their descriptor buffers straight into
+    the device matcher (exact L1, exact L2, tensor-core L2) -- same answers as the host entry point on the same descriptors."""
+    import torch
+
+    cap = 4096
+    st = torch.cuda.current_stream().cuda_stream
+    descs = []
+    for name in ("query_2448", "scene_960"):
+        img = torch.from_numpy(golden(name)["gray"].astype(np.float32)[None]).cuda()
+        d_kp = torch.zeros((1, cap, 28), dtype=torch.uint8, device="cuda")
+        d_desc = torch.zeros((1, cap, 128), dtype=torch.float32, device="cuda")
+        d_cnt = torch.zeros(1, dtype=torch.int32, device="cuda")
+        sift.detect_describe_batch_dev(img, d_kp, d_desc, d_cnt, cap, st)
+        n = int(d_cnt[0])
+        assert 0 < n <= cap
+        descs.append(d_desc[0, :n].contiguous())
+    dq, ds = descs
+    for norm, tc in ((pkg.NORM_L1, False), (pkg.NORM_L2, False), (pkg.NORM_L2, True)):
+        d_idx = torch.zeros((len(dq), 2), dtype=torch.int32, device="cuda")
+        d_dist = torch.zeros((len(dq), 2), dtype=torch.float32, device="cuda")
+        sift.match_knn2_dev(dq, ds, d_idx, d_dist, norm, tensor_cores=tc, stream=st)
+        torch.cuda.synchronize()
+        idx, dist, good = sift.match_knn2(dq.cpu().numpy(), ds.cpu().numpy(), norm, 0.86)
+        assert np.array_equal(d_idx.cpu().numpy(), idx) and np.array_equal(d_dist.cpu().numpy(), dist), (norm, tc)
+    assert good.sum() > 50  # the book cover is found in the scene
