@@ -6,7 +6,7 @@
 //
 // The reference scatters every window sample into a (4+2)x(4+2)x(8+2) histogram.  A scatter into one shared histogram
 // needs shared-memory float atomics, which on sm_100a are CAS loops (ATOMS.CAST.SPIN) that serialise badly because
-// neighbouring samples hit the same bins.  This kernel is atomics-free and deterministic, one CTA (128 threads) per
+// neighbouring samples hit the same bins.  This kernel is atomics-free and deterministic, one CTA (64 threads) per
 // keypoint, one pass:
 //   - the 4 cell-rows of the descriptor grid are split in two pairs p (a in {2p, 2p+1}); a 4-lane group owns (pair, window
 //     row): its lanes walk the row's j-interval 2p-1 <= rbin < 2p+2, -1 < cbin < 4 (two slab inequalities rounded
@@ -16,7 +16,7 @@
 //     own per-sample arithmetic done once per pixel), applies the Gaussian weight, and its trilinear votes that fall into the pair's cells go straight into THREAD-PRIVATE histograms
 //     [2 cell-rows][4 cells][9 bins] in shared memory (layout [bin][thread]: conflict-free plain read-modify-write).
 //     A sample is evaluated 1.2 times on average (twice only when its two cell-rows straddle the pairs);
-//   - tail: 128 threads = 128 output elements: sum the 64 private copies of the owning pair (rotated, conflict-free),
+//   - tail: sum the 32 private copies of each pair (rotated, conflict-free); a thread owns 2 of the 128 output elements;
 //     fold the circular bin, then L2 -> clamp 0.2 -> x512 -> uchar (round half even) -> L1 -> sqrt with block reductions.
 // Only the inner 4x4 cells are kept by the reference (:676-684), so the border cells are never formed.
 #include "sift_internal.cuh"
@@ -25,7 +25,14 @@ namespace siftb200 {
 namespace {
 
 constexpr int DW = 4, DB = 8;  // SIFT_DESCR_WIDTH, SIFT_DESCR_HIST_BINS (src/sift.cpp:12,15)
-constexpr int DT = 128;        // threads per CTA = output elements
+#ifndef DESC_DT
+#define DESC_DT 64
+#endif
+constexpr int DT = DESC_DT;    // threads per CTA.  Zeroing, interval tables, column sums and norms are per-warp costs paid once per keypoint:
+                               // measured 128 / 64 / 32 threads: 66.5 / 60.3 / 61.4 us per frame (32: too few row groups per pair, lower occupancy)
+constexpr int HALF = DT / 2;   // threads (= private histogram copies) per cell-row pair
+constexpr int NEL = 128 / DT;  // output elements per thread
+constexpr int CTAS_PER_SM = DT == 128 ? 6 : DT == 64 ? 10 : 18;  // what 227 KB of shared memory admits (38 KB / 21.6 KB per CTA)
 #ifndef DESC_GL
 #define DESC_GL 4
 #endif
@@ -39,14 +46,16 @@ constexpr int DESC_SMEM_BYTES = (PRIV_FLOATS + 2 * PRIV_BINS + 8) * 4 + 2 * 2 * 
 __device__ __forceinline__ int cv_round(float v) { return __float2int_rn(v); }
 __device__ __forceinline__ int cv_floor(float v) { return __float2int_rd(v); }
 
-// sum over the CTA (4 warps); every thread gets the result.  `red` = 4 floats of shared scratch.
+// sum over the CTA (DT/32 warps); every thread gets the result.  `red` = 4 floats of shared scratch.
 __device__ __forceinline__ float block_sum(float v, float* red, int tid) {
 #pragma unroll
     for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+    if (DT == 32) return v;
     __syncthreads();
     if ((tid & 31) == 0) red[tid >> 5] = v;
     __syncthreads();
-    return (red[0] + red[1]) + (red[2] + red[3]);
+    if (DT == 128) return (red[0] + red[1]) + (red[2] + red[3]);
+    return red[0] + red[1];
 }
 
 // window radius of calcSIFTDescriptor (:587-590)
@@ -94,7 +103,7 @@ __device__ void calc_descriptor(const float2* __restrict__ mo, int rows, int col
 
     for (int k = tid * 4; k < PRIV_FLOATS; k += DT * 4) *reinterpret_cast<float4*>(s_priv + k) = make_float4(0.f, 0.f, 0.f, 0.f);
     const int gl = tid & (GL - 1);
-    const int p = tid >> 6, slot = (tid & 63) / GL;  // cell-row pair (its 64 threads are contiguous), row slot (64/GL slots per pair)
+    const int p = tid / HALF, slot = (tid % HALF) / GL;  // cell-row pair (its HALF threads are contiguous), row slot (HALF/GL slots per pair)
     float* priv = s_priv + tid;
     for (int band0 = imin; band0 <= imax; band0 += NB) {
         const int nrows = min(NB, imax - band0 + 1);
@@ -113,7 +122,7 @@ __device__ void calc_descriptor(const float2* __restrict__ mo, int rows, int col
         // flattened walk: a group advances through its rows (slot, slot+8, ...) one 8-sample step per iteration (one sample per
         // lane), so the four groups of a warp never wait for each other at row boundaries; the NEXT step's gradient-map load is
         // issued before the current step's arithmetic (software pipeline).
-        int r = slot - 64 / GL, jb = 1, jhi = 0;
+        int r = slot - HALF / GL, jb = 1, jhi = 0;
         const float2* rowp = mo;
         float isin = 0.f, icos = 0.f;
         // advance (r, jb, jhi, rowp, isin, icos) to the next step; false when the group has no more work in this band
@@ -121,7 +130,7 @@ __device__ void calc_descriptor(const float2* __restrict__ mo, int rows, int col
             jb += GL;
             if (jb > jhi) {
                 do {
-                    r += 64 / GL;
+                    r += HALF / GL;
                     if (r >= nrows) return false;
                     jb = s_jlo[p * NB + r];
                     jhi = s_jhi[p * NB + r];
@@ -195,37 +204,52 @@ __device__ void calc_descriptor(const float2* __restrict__ mo, int rows, int col
         __syncthreads();
     }
 
-    // ---- tail, stage A: the 2 x 72 column sums over the 64 private copies of each pair (rotated read: conflict-free) ----
+    // ---- tail, stage A: the 2 x 72 column sums over the HALF private copies of each pair (rotated read: conflict-free) ----
     for (int sidx = tid; sidx < 2 * PRIV_BINS; sidx += DT) {
         const int sp = sidx >= PRIV_BINS, bin = sidx - sp * PRIV_BINS;
-        const float* col = s_priv + bin * DT + sp * (DT / 2);  // the 64 private copies of pair sp are contiguous
+        const float* col = s_priv + bin * DT + sp * HALF;  // the HALF private copies of pair sp are contiguous
         float acc = 0.f;
 #pragma unroll 16
-        for (int g = 0; g < DT / 2; ++g) acc += col[(g + tid) & (DT / 2 - 1)];
+        for (int g = 0; g < HALF; ++g) acc += col[(g + tid) & (HALF - 1)];
         s_sum[sidx] = acc;
     }
     __syncthreads();
-    // ---- stage B: thread = output element (cell*8 + k) ----
-    const int e_cell = tid >> 3, e_k = tid & 7;
-    const int e_a = e_cell >> 2, e_b = e_cell & 3;
-    const float* ssum = s_sum + (e_a >> 1) * PRIV_BINS + ((e_a & 1) * DW + e_b) * (DB + 1);
-    float v = ssum[e_k];
-    if (e_k == 0) v += ssum[DB];  // hist[idx] += hist[idx+n] (:680); hist[idx+n+1] is never written since o0 <= n-1
-    float nrm2 = block_sum(v * v, s_red, tid);
+    // ---- stage B: output element e = cell*8 + k; thread tid owns elements tid, tid + DT, ... ----
+    float v[NEL];
+    float part = 0.f;
+#pragma unroll
+    for (int q = 0; q < NEL; ++q) {
+        const int e = tid + q * DT;
+        const int e_cell = e >> 3, e_k = e & 7;
+        const int e_a = e_cell >> 2, e_b = e_cell & 3;
+        const float* ssum = s_sum + (e_a >> 1) * PRIV_BINS + ((e_a & 1) * DW + e_b) * (DB + 1);
+        v[q] = ssum[e_k];
+        if (e_k == 0) v[q] += ssum[DB];  // hist[idx] += hist[idx+n] (:680); hist[idx+n+1] is never written since o0 <= n-1
+        part += v[q] * v[q];
+    }
+    float nrm2 = block_sum(part, s_red, tid);
     const float thr = sqrtf(nrm2) * 0.2f;
-    v = fminf(v, thr);
-    nrm2 = block_sum(v * v, s_red, tid);
+    part = 0.f;
+#pragma unroll
+    for (int q = 0; q < NEL; ++q) { v[q] = fminf(v[q], thr); part += v[q] * v[q]; }
+    nrm2 = block_sum(part, s_red, tid);
     nrm2 = 512.f / fmaxf(sqrtf(nrm2), 1.1920928955078125e-7f);
-    int u = __float2int_rn(v * nrm2);  // saturate_cast<uchar>: round half to even, clamp to 0..255
-    u = min(max(u, 0), 255);
-    v = (float)u * nrm2;
-    float nrm1 = block_sum(v, s_red, tid);
+    part = 0.f;
+#pragma unroll
+    for (int q = 0; q < NEL; ++q) {
+        int u = __float2int_rn(v[q] * nrm2);  // saturate_cast<uchar>: round half to even, clamp to 0..255
+        u = min(max(u, 0), 255);
+        v[q] = (float)u * nrm2;
+        part += v[q];
+    }
+    float nrm1 = block_sum(part, s_red, tid);
     nrm1 = 1.f / fmaxf(nrm1, 1.1920928955078125e-7f);
-    dst[tid] = sqrtf(v * nrm1);
+#pragma unroll
+    for (int q = 0; q < NEL; ++q) dst[tid + q * DT] = sqrtf(v[q] * nrm1);
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(DT, 6)
+__global__ void __launch_bounds__(DT, CTAS_PER_SM)
     describe_kernel(const __grid_constant__ PyrView pv, const DetectBuf db, SiftKeypoint* __restrict__ kp_out, float* __restrict__ desc_out, int cap) {
     extern __shared__ float smem[];
     const int f = blockIdx.y;
@@ -290,7 +314,7 @@ void init_describe_kernels() {
 }
 
 int launch_describe(const PyrView& pv, const DetectBuf& db, int n_frames, SiftKeypoint* d_kp, float* d_desc, int cap, cudaStream_t st) {
-    dim3 grid(148 * 6, n_frames);
+    dim3 grid(148 * CTAS_PER_SM, n_frames);
     describe_kernel<<<grid, DT, DESC_SMEM_BYTES, st>>>(pv, db, d_kp, d_desc, cap);
     return 1;
 }
