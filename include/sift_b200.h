@@ -141,7 +141,8 @@ int sift_b200_match_knn2_ex(SiftB200* h, const float* query, int nq, const float
                             int32_t* idx_out, float* dist_out, uint8_t* good_out, int tensor_cores, float* kernel_ms);
 
 /* Device-resident form: d_query [nq x 128], d_train [nt x 128] float32 on the device, results d_idx / d_dist [nq x 2] on the device,
- * asynchronous on `stream` (scratch comes from the stream-ordered allocator).  The ratio test is left to the caller (two floats). */
+ * asynchronous on `stream`.  The tensor-core path keeps its scratch in the handle: calls on one handle must be ordered (same stream, or
+ * synchronised by the caller).  The ratio test is left to the caller (two floats). */
 int sift_b200_match_knn2_dev(SiftB200* h, const float* d_query, int nq, const float* d_train, int nt, int norm, int32_t* d_idx,
                              float* d_dist, int tensor_cores, void* stream);
 

@@ -52,6 +52,8 @@ struct SiftB200 {
     // second staging set + copy streams for the pipelined host-batch entry point
     float* d_img2 = nullptr;
     float* d_img3 = nullptr;  // third input buffer: lets the H2D copy run one chunk ahead of the two compute lanes
+    void* match_scratch = nullptr;   // operand tiles + shortlists of the tensor-core matcher, grown on demand
+    size_t match_scratch_bytes = 0;
     bool exact_pyramid = false;  // replay the reference's non-separable blur loop bit for bit (pyramid_exact.cu)
     bool taper = true;        // host batch: short chunks at both ends of a call (env SIFT_B200_TAPER=0 disables)
     SiftKeypoint* d_kp2 = nullptr;
@@ -360,6 +362,7 @@ int sift_b200_destroy(SiftB200* h) {
     for (auto& e : h->ev_join) if (e) cudaEventDestroy(e);
     cudaFree(h->d_img); cudaFree(h->d_kp); cudaFree(h->d_desc); cudaFree(h->d_counts);
     cudaFreeHost(h->h_counts);
+    cudaFree(h->match_scratch);
     cudaFree(h->d_img2); cudaFree(h->d_img3); cudaFree(h->d_kp2); cudaFree(h->d_desc2); cudaFree(h->d_counts2);
     if (h->h_counts2) cudaFreeHost(h->h_counts2);
     for (int b = 0; b < 3; ++b) for (cudaEvent_t e : {h->ev_in[b], h->ev_comp[b]}) if (e) cudaEventDestroy(e);
@@ -734,10 +737,14 @@ int sift_b200_match_knn2_dev(SiftB200* h, const float* d_query, int nq, const fl
     cudaStream_t st = (cudaStream_t)stream;
     // a train set shorter than the shortlist goes through the exact kernel (its -1 / +inf padding rule)
     if (tensor_cores && nt >= 4) {
-        void* scratch = nullptr;
-        CUDA_TRY(cudaMallocAsync(&scratch, match_tc_scratch_bytes(nq, nt), st));
-        h->launches += launch_match_tc(d_query, nq, d_train, nt, scratch, d_dist, d_idx, st);
-        CUDA_TRY(cudaFreeAsync(scratch, st));
+        const size_t need = match_tc_scratch_bytes(nq, nt);
+        if (need > h->match_scratch_bytes) {  // cudaFree synchronises the device: earlier matcher calls have finished with the old buffer
+            if (h->match_scratch) cudaFree(h->match_scratch);
+            h->match_scratch = nullptr; h->match_scratch_bytes = 0;
+            CUDA_TRY(cudaMalloc(&h->match_scratch, need));
+            h->match_scratch_bytes = need;
+        }
+        h->launches += launch_match_tc(d_query, nq, d_train, nt, h->match_scratch, d_dist, d_idx, st);
     } else {
         h->launches += launch_match(d_query, nq, d_train, nt, norm, d_dist, d_idx, st);
     }

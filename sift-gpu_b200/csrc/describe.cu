@@ -142,19 +142,24 @@ __device__ void calc_descriptor(const float2* __restrict__ mo, int rows, int col
             }
             return true;
         };
-        // three steps in flight: the gradient-map load of step k+2 is issued before the arithmetic of step k
-        struct Step { int j, jhi; float isin, icos; float2 mo; bool ok; };
+        // RING steps in flight: the gradient-map load of step k+RING-1 is issued before the arithmetic of step k.  A stage carries only
+        // {j, i*sin, i*cos, Mag/Ori}: j = J_IDLE marks a lane past the end of its row (any real rotation sends it far outside the window,
+        // so the reference's own range test rejects it), j = J_DONE a group that has run out of rows.
+        struct Step { int j; float isin, icos; float2 mo; };
+        constexpr int J_IDLE = 1 << 20, J_DONE = 0x7fffffff;
         auto issue = [&](Step& st) {
-            st.ok = advance();
             st.mo = make_float2(0.f, 0.f);
-            if (st.ok) {
-                st.j = jb + gl; st.jhi = jhi; st.isin = isin; st.icos = icos;
-                st.mo = __ldg(rowp + min(st.j, jmax));  // clamped: always an interior pixel
+            st.j = J_DONE;
+            if (advance()) {
+                const int j = jb + gl;
+                st.isin = isin; st.icos = icos;
+                st.mo = __ldg(rowp + min(j, jmax));  // clamped: always an interior pixel
+                st.j = j <= jhi ? j : J_IDLE;
             }
         };
         // one step: the eight trilinear votes of the sample of this lane (position/metadata/gradient in st)
         auto vote = [&](const Step& st) {
-            const int j = st.j, jhi_c = st.jhi;
+            const int j = st.j;
             const float isin_c = st.isin, icos_c = st.icos;
             const float2 cur = st.mo;
             {
@@ -162,7 +167,7 @@ __device__ void calc_descriptor(const float2* __restrict__ mo, int rows, int col
             const float r_rot = j * sin_t + icos_c;
             float rbin = r_rot + DW / 2 - 0.5f;
             float cbin = c_rot + DW / 2 - 0.5f;
-            const bool acc = j <= jhi_c && rbin > -1 && rbin < DW && cbin > -1 && cbin < DW;  // (:620)
+            const bool acc = rbin > -1 && rbin < DW && cbin > -1 && cbin < DW;  // (:620)
             const float w_ = expf((c_rot * c_rot + r_rot * r_rot) * exp_scale);
             float obin = (cur.y - ori) * bins_per_rad;
             const float mag = cur.x * w_;
@@ -190,16 +195,18 @@ __device__ void calc_descriptor(const float2* __restrict__ mo, int rows, int col
             }
         }
         };
-        // ring of three stages, unrolled by three so that a stage is refilled in place (no register shuffling)
-        Step s0, s1, s2;
-        issue(s0); issue(s1); issue(s2);
+        // ring of four stages, unrolled by four so that a stage is refilled in place (no register shuffling)
+        Step s0, s1, s2, s3;
+        issue(s0); issue(s1); issue(s2); issue(s3);
         for (;;) {
-            if (!s0.ok) break;
+            if (s0.j == J_DONE) break;
             vote(s0); issue(s0);
-            if (!s1.ok) break;
+            if (s1.j == J_DONE) break;
             vote(s1); issue(s1);
-            if (!s2.ok) break;
+            if (s2.j == J_DONE) break;
             vote(s2); issue(s2);
+            if (s3.j == J_DONE) break;
+            vote(s3); issue(s3);
         }
         __syncthreads();
     }

@@ -28,7 +28,8 @@ for r in rows[hi + 1:]:
     n = int(r[c["Instructions Executed"]] or 0)
     s = int(r[c["# Samples"]] or 0)
     mix[op] += n; samples[op] += s; tot += n
-    wave[op] += int(r[c["L1 Wavefronts Shared"]] or 0); ideal[op] += int(r[c["L1 Wavefronts Shared Ideal"]] or 0)
+    if "L1 Wavefronts Shared" in c:  # absent for kernels without shared-memory traffic
+        wave[op] += int(r[c["L1 Wavefronts Shared"]] or 0); ideal[op] += int(r[c["L1 Wavefronts Shared Ideal"]] or 0)
     lines.append((s, n, src))
 ts = sum(samples.values())
 print(f"total warp-instructions {tot/1e6:.1f} M, samples {ts}")
