@@ -41,7 +41,11 @@ constexpr int PRIV_BINS = 2 * DW * (DB + 1);      // private histogram of one th
 constexpr int TRASH = PRIV_BINS;                   // private trash bins that swallow votes for cells outside the pair / the 4x4 grid
 constexpr int PRIV_FLOATS = (PRIV_BINS + 2) * DT;  // + two trash rows (a vote updates bins i and i+1)
 constexpr int NB = 128;                            // window rows per band (intervals of one band live in shared memory)
-constexpr int DESC_SMEM_BYTES = (PRIV_FLOATS + 2 * PRIV_BINS + 8) * 4 + 2 * 2 * NB * 4;
+// Interval tables are 32-bit on purpose: the same kernel with 16-bit tables measured 141 us instead of 58 us per frame (twice, in two
+// different versions of this kernel; cause not found), and aliasing them with the column sums to fit an 11th CTA per SM gained nothing.
+typedef int tab_t;
+constexpr int TAB_BYTES = 2 * 2 * NB * (int)sizeof(tab_t), SUM_BYTES = (2 * PRIV_BINS + 8) * 4;
+constexpr int DESC_SMEM_BYTES = PRIV_FLOATS * 4 + SUM_BYTES + TAB_BYTES;
 
 __device__ __forceinline__ int cv_round(float v) { return __float2int_rn(v); }
 __device__ __forceinline__ int cv_floor(float v) { return __float2int_rd(v); }
@@ -92,10 +96,10 @@ __device__ void calc_descriptor(const float2* __restrict__ mo, int rows, int col
     cos_t /= hist_width;
     sin_t /= hist_width;
     float* s_priv = smem;                      // [PRIV_BINS + trash][DT]
-    float* s_sum = smem + PRIV_FLOATS;         // [2 pairs][PRIV_BINS] column sums
+    float* s_sum = smem + PRIV_FLOATS;         // [2 pairs][PRIV_BINS] column sums (tail only)
     float* s_red = s_sum + 2 * PRIV_BINS;      // 8 floats
-    int* s_jlo = reinterpret_cast<int*>(s_red + 8);  // [2 pairs][NB]
-    int* s_jhi = s_jlo + 2 * NB;
+    tab_t* s_jlo = reinterpret_cast<tab_t*>(s_red + 8);  // [2 pairs][NB]
+    tab_t* s_jhi = s_jlo + 2 * NB;
     const float inv_s = fabsf(sin_t) > 1e-6f ? 1.f / sin_t : 0.f;
     const float inv_c = fabsf(cos_t) > 1e-6f ? 1.f / cos_t : 0.f;
     const int jmin = max(-radius, 1 - px), jmax = min(radius, cols - 2 - px);   // 0 < c < cols-1  (:621)
@@ -115,8 +119,8 @@ __device__ void calc_descriptor(const float2* __restrict__ mo, int rows, int col
             ok = ok && slab(cos_t, inv_c, -(i * sin_t) + 1.5f, -1.f, 4.f, lo, hi);
             // floor/ceil of the real-valued slab bounds already cover every sample the float test can accept (the bounds are
             // accurate to ~1e-5 px; a sample that close to the boundary carries a ~1e-6 share of its vote)
-            s_jlo[pp * NB + it - pp * nrows] = ok ? max(jmin, (int)floorf(lo)) : 1;
-            s_jhi[pp * NB + it - pp * nrows] = ok ? min(jmax, (int)ceilf(hi)) : 0;
+            s_jlo[pp * NB + it - pp * nrows] = (tab_t)(ok ? max(jmin, (int)floorf(lo)) : 1);
+            s_jhi[pp * NB + it - pp * nrows] = (tab_t)(ok ? min(jmax, (int)ceilf(hi)) : 0);
         }
         __syncthreads();
         // flattened walk: a group advances through its rows (slot, slot+8, ...) one 8-sample step per iteration (one sample per
@@ -256,7 +260,7 @@ __device__ void calc_descriptor(const float2* __restrict__ mo, int rows, int col
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(DT, CTAS_PER_SM)
+__global__ void __maxnreg__(DT == 64 ? 88 : DT == 128 ? 80 : 112)
     describe_kernel(const __grid_constant__ PyrView pv, const DetectBuf db, SiftKeypoint* __restrict__ kp_out, float* __restrict__ desc_out, int cap) {
     extern __shared__ float smem[];
     const int f = blockIdx.y;
