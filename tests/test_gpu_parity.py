@@ -181,6 +181,16 @@ def test_tensor_core_matcher_identical_indices(sift, pkg, oracle, golden):
             keep = np.ones(nq, bool)
         assert np.array_equal(gi[keep], ei[keep]) and np.array_equal(gd[keep], ed[keep]) and np.array_equal(gg[keep], eg[keep])
         assert np.array_equal(gi[keep], oi[keep]) and np.array_equal(gg[keep], og[keep])
+    # other value ranges: raw (unnormalised) SIFT-like integers 0..255, signed data, tiny magnitudes, zero rows -- the error bound and
+    # the integer sort keys of the tensor path scale with |q|^2 + |t|^2, not with an absolute constant
+    for make in (lambda n: rng.integers(0, 256, size=(n, 128)).astype(np.float32),
+                 lambda n: rng.standard_normal((n, 128)).astype(np.float32) * 30.0,
+                 lambda n: (rng.random((n, 128)) * 1e-6).astype(np.float32)):
+        q, t = make(700), make(900)
+        t[17] = q[3]; t[400] = q[3]; q[9] = 0.0; t[5] = 0.0
+        gi, gd, gg = sift.match_knn2(q, t, pkg.NORM_L2, 0.86, tensor_cores=True)
+        ei, ed, eg = sift.match_knn2(q, t, pkg.NORM_L2, 0.86)
+        assert np.array_equal(gi, ei) and np.array_equal(gd, ed) and np.array_equal(gg, eg)
     with pytest.raises(pkg.SiftError):
         sift.match_knn2(q, t, pkg.NORM_L1, 0.86, tensor_cores=True)
 
