@@ -311,27 +311,38 @@ __global__ void __launch_bounds__(ORI_WARPS * 32) orientation_kernel(const __gri
             const int total = (i_hi - i_lo + 1) * wj;
             const float2* base = mo + (size_t)py * pitch + px;
             int ci = i_lo + lane / wj, cj = j_lo + lane % wj;  // running (row, col) of this lane's next sample, advanced by 32 without divisions
-            for (int idx0 = lane; idx0 < total; idx0 += 128) {
-                int ii[4], jj[4];
-                float2 g[4];
+            // software pipeline: the four loads of batch k+1 are issued before the votes of batch k (ncu: with one batch in flight, 46 %
+            // of the kernel's stall samples sat on the first use of the gathered values)
+            struct Batch { int ii[4], jj[4]; float2 g[4]; };
+            auto fetch = [&](Batch& b, int idx0) {
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    ii[u] = ci; jj[u] = cj;
-                    g[u] = make_float2(0.f, 0.f);
-                    if (idx0 + 32 * u < total) g[u] = __ldg(base + (ptrdiff_t)ci * pitch + cj);
+                    b.ii[u] = ci; b.jj[u] = cj;
+                    b.g[u] = make_float2(0.f, 0.f);
+                    if (idx0 + 32 * u < total) b.g[u] = __ldg(base + (ptrdiff_t)ci * pitch + cj);
                     cj += 32;
                     while (cj > j_hi) { cj -= wj; ++ci; }
                 }
+            };
+            auto vote = [&](const Batch& b, int idx0) {
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     if (idx0 + 32 * u < total) {
-                        const float wgt = expf((ii[u] * ii[u] + jj[u] * jj[u]) * expf_scale);
-                        int bin = cv_round((kOriBins / 360.f) * g[u].y);
+                        const float wgt = expf((b.ii[u] * b.ii[u] + b.jj[u] * b.jj[u]) * expf_scale);
+                        int bin = cv_round((kOriBins / 360.f) * b.g[u].y);
                         if (bin >= kOriBins) bin -= kOriBins;
                         if (bin < 0) bin += kOriBins;
-                        priv[bin * 32] += wgt * g[u].x;
+                        priv[bin * 32] += wgt * b.g[u].x;
                     }
                 }
+            };
+            Batch b0, b1;
+            fetch(b0, lane);
+            for (int idx0 = lane; idx0 < total; idx0 += 256) {
+                fetch(b1, idx0 + 128);   // past the end: no loads, only index bookkeeping
+                vote(b0, idx0);
+                fetch(b0, idx0 + 256);
+                vote(b1, idx0 + 128);
             }
         }
         (void)w;
