@@ -87,3 +87,21 @@ def test_upsample2x_restatement_matches_cv2(synth):
         got = synth.upsample2x(img)
         want = cv2.resize(img, (2 * shape[1], 2 * shape[0]), interpolation=cv2.INTER_LINEAR)
         assert got.shape == want.shape and np.abs(got - want).max() <= 1e-4
+
+
+def test_bind_near_gpu_is_harmless_without_nvml():
+    """bench.bind_near_gpu pins the process to the GPU-local CPUs before the pinned host buffers are allocated; without a GPU / NVML it
+    must change nothing and say so."""
+    import os
+
+    import bench
+
+    before = os.sched_getaffinity(0)
+    prev, n = bench.bind_near_gpu(0)
+    after = os.sched_getaffinity(0)
+    if prev is None:
+        assert n == 0 and after == before
+    else:  # a box with NVML: bound to a non-empty subset, and the caller can restore
+        assert 0 < n <= len(before) and after <= before
+        os.sched_setaffinity(0, prev)
+        assert os.sched_getaffinity(0) == before
