@@ -396,6 +396,15 @@ def run_ours(args, out):
         extras["exact_pyramid"] = {"value": nx / (time.perf_counter() - t0), "unit": "frames/s",
                                    "note": "pyramid bit-identical to the reference (non-separable loop replayed); validation mode"}
         s.set_exact_pyramid(False)
+        # (3) what the reference's driver does: ONE image through SIFT_NCL, host buffers in and out (sift_b200_detect_describe)
+        one = host_frames[0].numpy()
+        lat = []
+        for _ in range(12):
+            t0 = time.perf_counter()
+            kp1, desc1 = s.detect_describe(one)
+            lat.append(time.perf_counter() - t0)
+        extras["single_frame_latency"] = {"value": round(1e3 * float(np.median(lat[2:])), 3), "unit": "ms", "keypoints": int(len(kp1)),
+                                          "api": "sift_b200_detect_describe (one 1080p float32 host image in, host keypoints + descriptors out)"}
         rng = np.random.default_rng(5)
         qd = np.sqrt(rng.dirichlet(np.full(128, 0.6), 1358)).astype(np.float32)
         td = np.sqrt(rng.dirichlet(np.full(128, 0.6), 1444)).astype(np.float32)
