@@ -134,9 +134,10 @@ int sift_b200_cal_descriptor(SiftB200* h, const float* gpyr, int rows, int cols,
 int sift_b200_match_knn2(SiftB200* h, const float* query, int nq, const float* train, int nt, int norm, double ratio,
                          int32_t* idx_out, float* dist_out, uint8_t* good_out);
 /* Same call with two extras.  tensor_cores != 0 (NORM_L2 only): distances come from split-bf16 tcgen05 MMAs (fp32 accumulation in
- * TMEM), a short list of candidates per query is re-ranked exactly in fp64, so the result equals the exact kernel's unless several
- * train rows of one 32-row chunk lie within ~3e-5 of a true neighbour's distance.  kernel_ms (optional): CUDA-event time of the
- * kernels alone. */
+ * TMEM), a short list of candidates per query is re-ranked exactly in fp64.  A query whose short list is not provably complete
+ * (three or more train rows within the ~3e-5 error of the split products of its second neighbour) is detected and matched against
+ * every train row exactly, so indices, distances and tie order ALWAYS equal the exact kernel's.  kernel_ms (optional): CUDA-event
+ * time of the kernels alone. */
 int sift_b200_match_knn2_ex(SiftB200* h, const float* query, int nq, const float* train, int nt, int norm, double ratio,
                             int32_t* idx_out, float* dist_out, uint8_t* good_out, int tensor_cores, float* kernel_ms);
 
@@ -145,6 +146,11 @@ int sift_b200_match_knn2_ex(SiftB200* h, const float* query, int nq, const float
  * synchronised by the caller).  The ratio test is left to the caller (two floats). */
 int sift_b200_match_knn2_dev(SiftB200* h, const float* d_query, int nq, const float* d_train, int nt, int norm, int32_t* d_idx,
                              float* d_dist, int tensor_cores, void* stream);
+
+/* Chunk schedule of the host-batch entry points for n_frames frames on a handle created with max_batch (pure host logic, no
+ * device needed): writes up to plan_cap chunk sizes, returns the number of chunks (or -1 on a bad argument).  Every chunk is in
+ * [1, max_batch] and the chunks sum to n_frames; with taper != 0 the first and last chunks are short (max_batch/8, /4, /2). */
+int sift_b200_chunk_plan(int n_frames, int max_batch, int taper, int* plan_out, int plan_cap);
 
 /* ---- introspection for the benchmark ------------------------------------------------------------ */
 /* Kernel launches issued by this handle since creation (bench.py reports the delta as gpu_launches). */

@@ -32,7 +32,7 @@ ABI_SYMBOLS = [
     "sift_b200_detect_describe_batch_host_u8", "sift_b200_detect_describe_batch_dev_u8", "sift_b200_rgb2gray_u8_dev", "sift_b200_upsample2x_dev", "sift_b200_detect_describe_up2", "sift_b200_gaussian_blur", "sift_b200_gaussian_blur_1d",
     "sift_b200_build_gaussian_pyramid", "sift_b200_build_dog_pyramid", "sift_b200_find_scale_space_extrema",
     "sift_b200_cal_descriptor", "sift_b200_match_knn2", "sift_b200_match_knn2_ex", "sift_b200_match_knn2_dev", "sift_b200_set_exact_pyramid", "sift_b200_launch_count", "sift_b200_set_stage_timing",
-    "sift_b200_get_stage_ms",
+    "sift_b200_get_stage_ms", "sift_b200_chunk_plan",
 ]
 
 
@@ -56,6 +56,15 @@ def lib() -> C.CDLL:
         _lib.sift_b200_version.restype = C.c_char_p
         _lib.sift_b200_launch_count.restype = C.c_longlong
     return _lib
+
+
+def chunk_plan(n_frames: int, max_batch: int, taper: bool = True):
+    """Chunk schedule of the host-batch entry points (host logic only: works without a GPU)."""
+    buf = (C.c_int * (n_frames + 16))()
+    n = lib().sift_b200_chunk_plan(n_frames, max_batch, int(taper), buf, len(buf))
+    if n < 0:
+        raise ValueError("bad chunk_plan argument")
+    return list(buf[:n])
 
 
 def _p(a):

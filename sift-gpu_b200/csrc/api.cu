@@ -29,6 +29,19 @@ int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 int round_up(int v, int m) { return (v + m - 1) / m * m; }
 }  // namespace
 
+namespace siftb200 {
+int num_sms() {
+    static int cached[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (!cached[dev]) {
+        int n = 0;
+        cached[dev] = (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) ? n : 148;
+    }
+    return cached[dev];
+}
+}  // namespace siftb200
+
 struct SiftB200 {
     int device = 0, max_rows = 0, max_cols = 0, max_batch = 0, cap_kp = 0;
     cudaStream_t stream = nullptr;
@@ -424,8 +437,14 @@ static int ensure_pipeline(SiftB200* h) {
 static std::vector<int> chunk_plan(int n_frames, int max_batch, bool taper) {
     std::vector<int> head, plan;
     int rem = n_frames;
-    if (taper && n_frames >= 3 * max_batch)
-        for (int sz = max_batch / 8 > 0 ? max_batch / 8 : 1; sz < max_batch; sz *= 2) head.push_back(sz);
+    if (taper && n_frames >= 3 * max_batch) {
+        // a head size is used at both ends; keep at least one full chunk in the middle (rem stays >= max_batch > 0)
+        int used = 0;
+        for (int sz = max_batch / 8 > 0 ? max_batch / 8 : 1; sz < max_batch && 2 * (used + sz) + max_batch <= n_frames; sz *= 2) {
+            head.push_back(sz);
+            used += sz;
+        }
+    }
     for (int sz : head) { plan.push_back(sz); rem -= 2 * sz; }
     if (rem % max_batch) { plan.push_back(rem % max_batch); rem -= rem % max_batch; }
     for (; rem > 0; rem -= max_batch) plan.push_back(max_batch);
@@ -791,6 +810,13 @@ int sift_b200_match_knn2(SiftB200* h, const float* query, int nq, const float* t
 }
 
 long long sift_b200_launch_count(const SiftB200* h) { return h ? h->launches : 0; }
+
+int sift_b200_chunk_plan(int n_frames, int max_batch, int taper, int* plan_out, int plan_cap) {
+    if (n_frames < 0 || max_batch < 1 || (plan_cap > 0 && !plan_out)) return -1;
+    const std::vector<int> plan = chunk_plan(n_frames, max_batch, taper != 0);
+    for (size_t k = 0; k < plan.size() && (int)k < plan_cap; ++k) plan_out[k] = plan[k];
+    return (int)plan.size();
+}
 
 int sift_b200_set_exact_pyramid(SiftB200* h, int on) {
     if (!h) return fail(SIFT_B200_ERR_ARG, "null handle");

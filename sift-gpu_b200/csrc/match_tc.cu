@@ -22,9 +22,13 @@
 //      with a warp reduction and evaluates exactly (fp64, like match.cu) only the entries whose lower bound d2 - e does not exceed
 //      it -- usually two or three -- then emits the best two.
 // With exact arithmetic the two nearest rows of a split are always in its shortlist.  With the ~3e-5 error of the split products a
-// true top-2 neighbour can only be lost if three or more rows of ONE 32-row chunk, or the minima of five or more chunks, sit within
-// that error of it (exact duplicates of one chunk are safe: equal rows give equal keys and the lower columns win); the tests
-// compare with the exact matcher, the oracle and the reference fixture.  Every mbarrier wait is bounded and traps.
+// true top-2 neighbour could be lost if three or more rows of ONE 32-row chunk, or the minima of five or more chunks, sit within
+// that error of it.  That case is DETECTED, not tolerated: every (query, split) also records the smallest approximate distance any
+// row OUTSIDE its shortlist can have (min of the kept chunks' second minima and the fourth chunk minimum); if that bound minus the
+// worst-case error reaches the query's second-smallest upper bound, the shortlist is not provably complete and rerank_kernel
+// evaluates that query against every train row exactly.  The result is therefore always the exact kernel's (identical indices,
+// distances and tie order); the tests compare with the exact matcher, the oracle and the reference fixture.  Every mbarrier wait is
+// bounded and traps.
 #include <cuda_bf16.h>
 
 #include "sift_internal.cuh"
@@ -38,6 +42,7 @@ constexpr int OPER_BYTES = (DK / 8) * CHUNK_BYTES;   // 32 KB per operand matrix
 constexpr int TILE_BYTES = 2 * OPER_BYTES + TN * 4;  // hi | lo | norms
 constexpr int NCHUNK = 4;                            // chunks (32 train rows) kept per (query, train split)
 constexpr int SHORT = 2 * NCHUNK;                    // shortlist entries per (query, train split): two per kept chunk
+constexpr int SLOTS = SHORT + 1;                     // + one record {idx -1, d2 = lower bound of every approximate distance outside the shortlist}
 struct Cand { int32_t idx; float d2, e; };           // train row, approximate squared distance, bound on its error
 constexpr int NSTAGE = 2;
 constexpr int TC_THREADS = 192;
@@ -84,7 +89,7 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
 // block = one 128-row tile, 512 threads: thread (row, quarter) converts 32 of the row's 128 floats; all 8 float4 loads are issued first.
 // Blocks [0, q_blocks) convert the query matrix, the rest the train matrix (whose tiles follow the query tiles in `tiles`).
 __global__ void __launch_bounds__(512) prep_kernel(const float* __restrict__ q, int nq, const float* __restrict__ t, int nt, int q_blocks,
-                                                   uint8_t* __restrict__ tiles) {
+                                                   uint8_t* __restrict__ tiles, int* __restrict__ tn_max_bits) {
     __shared__ float part[4][TM];
     const bool is_q = (int)blockIdx.x < q_blocks;
     const float* src = is_q ? q : t;
@@ -117,7 +122,17 @@ __global__ void __launch_bounds__(512) prep_kernel(const float* __restrict__ q, 
     part[qtr][row] = s;
     __syncthreads();
     // rows past the end of the matrix get norm = +inf: as train rows they can never enter a shortlist, so the epilogue needs no column mask
-    if (qtr == 0) reinterpret_cast<float*>(hi + 2 * OPER_BYTES)[row] = grow < n ? (part[0][row] + part[1][row]) + (part[2][row] + part[3][row]) : INFINITY;
+    if (qtr == 0) {
+        const float nrm = (part[0][row] + part[1][row]) + (part[2][row] + part[3][row]);
+        reinterpret_cast<float*>(hi + 2 * OPER_BYTES)[row] = grow < n ? nrm : INFINITY;
+        // largest squared train norm (non-negative floats order like their bit patterns): bounds the error of rows outside a shortlist
+        if (!is_q && grow < n) {
+            int m = __float_as_int(nrm);
+#pragma unroll
+            for (int sft = 16; sft > 0; sft >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, sft));
+            if ((threadIdx.x & 31) == 0) atomicMax(tn_max_bits, m);
+        }
+    }
 }
 
 // ---- 2. tensor-core shortlist ---------------------------------------------------------------------------------------------------
@@ -281,9 +296,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) match_tc_kernel(const uint8_t* 
                         cd.d2 = __int_as_float(key & ~31) - bias;
                         cd.e = 6.103515625e-5f * (qn + tn) + 1e-30f;  // 2^-14 (|q|^2 + |t|^2): split products + the 5 key bits
                     }
-                    cand[((size_t)(q0 + row) * gridDim.y + blockIdx.y) * SHORT + 2 * j + h] = cd;
+                    cand[((size_t)(q0 + row) * gridDim.y + blockIdx.y) * SLOTS + 2 * j + h] = cd;
                 }
             }
+            // every train row of this split that is NOT in the shortlist has an approximate key >= its chunk's second minimum (kept
+            // chunks) or >= the largest kept chunk minimum (other chunks)
+            int bkey = Lk[NCHUNK - 1];
+#pragma unroll
+            for (int j = 0; j < NCHUNK; ++j) bkey = min(bkey, Ls[j]);
+            Cand bd;
+            bd.idx = -1; bd.e = 0.f;
+            bd.d2 = bkey == 0x7FFFFFFF ? INFINITY : __int_as_float(bkey & ~31) - bias;
+            cand[((size_t)(q0 + row) * gridDim.y + blockIdx.y) * SLOTS + SHORT] = bd;
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;");
@@ -295,17 +319,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) match_tc_kernel(const uint8_t* 
 }
 
 // ---- 3. exact fp64 re-rank: warp per query ----------------------------------------------------------------------------------------
-// Pass 1 (lanes over the shortlist entries): U2 = second-smallest upper bound d2 + e.  Pass 2: every entry with d2 - e <= U2 could
-// still be one of the two nearest; those are evaluated exactly, lane = 4 of the 128 components (same arithmetic as match.cu).
-__global__ void __launch_bounds__(256) rerank_kernel(const float* __restrict__ q, int nq, const float* __restrict__ t, const Cand* __restrict__ cand,
-                                                     int n_cand, float* __restrict__ dist, int32_t* __restrict__ idx) {
+// Pass 1 (lanes over the shortlist entries): U2 = second-smallest upper bound d2 + e.  Completeness check: a row outside the
+// shortlists has approximate distance >= its split's bound record and error <= e_max = 2^-14 (|q|^2 + max |t|^2); if bound - e_max
+// <= U2 for any split, such a row could still be one of the two nearest and the query is matched against ALL train rows instead.
+// Pass 2: every entry with d2 - e <= U2 could still be one of the two nearest; those are evaluated exactly, lane = 4 of the 128
+// components (same arithmetic as match.cu).
+__global__ void __launch_bounds__(256) rerank_kernel(const float* __restrict__ q, int nq, const float* __restrict__ t, int nt, const Cand* __restrict__ cand,
+                                                     int n_cand, const int* __restrict__ tn_max_bits, float* __restrict__ dist, int32_t* __restrict__ idx,
+                                                     int* __restrict__ n_fallback) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int i = blockIdx.x * 8 + warp;
     if (i >= nq) return;
     const Cand* mine = cand + (size_t)i * n_cand;
     float u1 = 3.4e38f, u2 = 3.4e38f;  // the two smallest upper bounds seen by this lane
+    float bound = INFINITY;            // smallest "outside the shortlist" bound over the splits
     for (int k = lane; k < n_cand; k += 32) {
         const Cand c = mine[k];
+        if (k % SLOTS == SHORT) bound = fminf(bound, c.d2);
         if (c.idx < 0) continue;
         const float u = c.d2 + c.e;
         if (u < u1) { u2 = u1; u1 = u; } else if (u < u2) u2 = u;
@@ -315,28 +345,41 @@ __global__ void __launch_bounds__(256) rerank_kernel(const float* __restrict__ q
         const float v1 = __shfl_xor_sync(0xffffffffu, u1, s), v2 = __shfl_xor_sync(0xffffffffu, u2, s);
         const float n1 = fminf(u1, v1), n2 = fminf(fmaxf(u1, v1), fminf(u2, v2));
         u1 = n1; u2 = n2;
+        bound = fminf(bound, __shfl_xor_sync(0xffffffffu, bound, s));
     }
     const float4 a = __ldg(reinterpret_cast<const float4*>(q + (size_t)i * 128) + lane);
+    float qn = a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w;
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) qn += __shfl_xor_sync(0xffffffffu, qn, s);
+    const float e_max = 6.103515625e-5f * (qn * 1.0001f + __int_as_float(*tn_max_bits)) + 1e-30f;
+    const bool complete = bound - e_max > u2;  // false also when fewer than two entries exist (u2 = 3.4e38)
     double b0 = INFINITY, b1 = INFINITY;
     int i0 = -1, i1 = -1;
-    for (int k0 = 0; k0 < n_cand; k0 += 32) {
-        Cand c; c.idx = -1; c.d2 = 0.f; c.e = 0.f;
-        if (k0 + lane < n_cand) c = mine[k0 + lane];
-        unsigned todo = __ballot_sync(0xffffffffu, c.idx >= 0 && c.d2 - c.e <= u2);
-        while (todo) {
-            const int src = __ffs(todo) - 1;
-            todo &= todo - 1;
-            const int j = __shfl_sync(0xffffffffu, c.idx, src);
-            const float4 b = __ldg(reinterpret_cast<const float4*>(t + (size_t)j * 128) + lane);
-            const double e0 = (double)a.x - (double)b.x, e1 = (double)a.y - (double)b.y, e2 = (double)a.z - (double)b.z, e3 = (double)a.w - (double)b.w;
-            double d = e0 * e0 + e1 * e1 + e2 * e2 + e3 * e3;
+    auto consider = [&](int j) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(t + (size_t)j * 128) + lane);
+        const double e0 = (double)a.x - (double)b.x, e1 = (double)a.y - (double)b.y, e2 = (double)a.z - (double)b.z, e3 = (double)a.w - (double)b.w;
+        double d = e0 * e0 + e1 * e1 + e2 * e2 + e3 * e3;
 #pragma unroll
-            for (int s = 16; s > 0; s >>= 1) d += __shfl_xor_sync(0xffffffffu, d, s);
-            d = sqrt(d);
-            // ascending distance, exact ties to the lower train index (BFMatcher order)
-            if (d < b0 || (d == b0 && j < i0)) { b1 = b0; i1 = i0; b0 = d; i0 = j; }
-            else if (d < b1 || (d == b1 && j < i1)) { b1 = d; i1 = j; }
+        for (int s = 16; s > 0; s >>= 1) d += __shfl_xor_sync(0xffffffffu, d, s);
+        d = sqrt(d);
+        // ascending distance, exact ties to the lower train index (BFMatcher order)
+        if (d < b0 || (d == b0 && j < i0)) { b1 = b0; i1 = i0; b0 = d; i0 = j; }
+        else if (d < b1 || (d == b1 && j < i1)) { b1 = d; i1 = j; }
+    };
+    if (complete) {
+        for (int k0 = 0; k0 < n_cand; k0 += 32) {
+            Cand c; c.idx = -1; c.d2 = 0.f; c.e = 0.f;
+            if (k0 + lane < n_cand) c = mine[k0 + lane];
+            unsigned todo = __ballot_sync(0xffffffffu, c.idx >= 0 && c.d2 - c.e <= u2);
+            while (todo) {
+                const int src = __ffs(todo) - 1;
+                todo &= todo - 1;
+                consider(__shfl_sync(0xffffffffu, c.idx, src));
+            }
         }
+    } else {
+        for (int j = 0; j < nt; ++j) consider(j);
+        if (lane == 0 && n_fallback) atomicAdd(n_fallback, 1);
     }
     if (lane == 0) {
         dist[2 * i] = (float)b0; dist[2 * i + 1] = (float)b1;
@@ -355,7 +398,7 @@ int match_tc_splits(int nq, int nt) {
     int best = 1;
     double best_cost = 1e30;
     for (int s = 1; s <= tt && s <= 64; ++s) {
-        const int waves = (qt * s + kNumSMs - 1) / kNumSMs;
+        const int waves = (qt * s + num_sms() - 1) / num_sms();
         const double cost = waves * ((tt + s - 1) / s + 2.0);
         if (cost < best_cost) { best_cost = cost; best = s; }
     }
@@ -364,7 +407,7 @@ int match_tc_splits(int nq, int nt) {
 
 size_t match_tc_scratch_bytes(int nq, int nt) {
     const size_t qt = (nq + TM - 1) / TM, tt = (nt + TN - 1) / TN;
-    return (qt + tt) * (size_t)TILE_BYTES + (size_t)nq * match_tc_splits(nq, nt) * SHORT * sizeof(Cand);
+    return (qt + tt) * (size_t)TILE_BYTES + (size_t)nq * match_tc_splits(nq, nt) * SLOTS * sizeof(Cand) + 16;
 }
 
 // L2 only.  d_scratch: match_tc_scratch_bytes(nq, nt) bytes, 128-byte aligned (operand tiles, then the shortlists).
@@ -375,9 +418,11 @@ int launch_match_tc(const float* d_q, int nq, const float* d_t, int nt, void* d_
     uint8_t* q_tiles = static_cast<uint8_t*>(d_scratch);
     uint8_t* t_tiles = q_tiles + (size_t)qt * TILE_BYTES;
     Cand* cand = reinterpret_cast<Cand*>(t_tiles + (size_t)tt * TILE_BYTES);
-    prep_kernel<<<qt + tt, 512, 0, st>>>(d_q, nq, d_t, nt, qt, q_tiles);
+    int* words = reinterpret_cast<int*>(cand + (size_t)nq * splits * SLOTS);  // [0] max squared train norm (float bits), [1] queries matched exhaustively
+    cudaMemsetAsync(words, 0, 8, st);
+    prep_kernel<<<qt + tt, 512, 0, st>>>(d_q, nq, d_t, nt, qt, q_tiles, words);
     match_tc_kernel<<<dim3(qt, splits), TC_THREADS, TC_SMEM_BYTES, st>>>(q_tiles, nq, t_tiles, nt, cand);
-    rerank_kernel<<<(nq + 7) / 8, 256, 0, st>>>(d_q, nq, d_t, cand, splits * SHORT, d_dist, d_idx);
+    rerank_kernel<<<(nq + 7) / 8, 256, 0, st>>>(d_q, nq, d_t, nt, cand, splits * SLOTS, words, d_dist, d_idx, words + 1);
     return 3;
 }
 

@@ -21,7 +21,6 @@ constexpr int kImgBorder = 5;      // src/sift.cpp:21
 constexpr int kMaxInterpSteps = 5; // src/sift.cpp:24
 constexpr int kOriBins = 36;       // src/sift.cpp:27
 constexpr int kMaxPeaks = 18;      // strict local maxima of a 36-bin circular histogram
-constexpr int kNumSMs = 148;      // B200
 constexpr int kMaxRadius = 18;     // floor(3*sig[4]) = floor(3*6.196774)
 
 struct OctaveView {
@@ -70,6 +69,7 @@ struct DetectBuf {
 // Blur taps: c_taps[0] = base sigma sqrt(1.6^2+0.2^2), c_taps[1..4] = sig[1..4] (src/sift.cpp:237-245).
 // 1-D factor of the reference's 2-D kernel: exp(-i^2/den)/sqrt(2 PI sigma^2), den = float(2*sigma*sigma).
 constexpr int kTapStride = 40;
+int num_sms();  // multiProcessorCount of the current device (148 on B200), cached per device
 void upload_taps(const float host_taps[5][kTapStride]);
 void init_pyramid_kernels();
 void init_detect_kernels();

@@ -60,6 +60,21 @@ def main():
     query = read_image("query.jpg", False)
     kq, dq = ref.sift_ncl(query.astype(np.float32))
     print("query native keypoints", len(kq))
+    # pre-quantisation descriptor vectors (the float value each component has just before saturate_cast<uchar>, src/sift.cpp:709):
+    # the unmodified reference does not expose them, so they come from the C port -- legitimate only because the port's keypoints and
+    # descriptors are bit-identical to oracle/_ref's on the very same image, which is asserted here before anything is written.
+    port = O.f32()
+    for tag, img, k_ref, d_ref in (("scene_960", scene, ks, ds), ("query_2448", query, kq, dq)):
+        kp_p, d_p, _, _, pq = port.sift_ncl(img.astype(np.float32), want_pyramids=True, want_prequant=True)
+        assert kp_p.tobytes() == k_ref.tobytes() and np.array_equal(d_p, d_ref), tag
+        np.savez_compressed(os.path.join(HERE, tag + "_prequant.npz"), prequant=pq.astype(np.float32))
+    # config 1, native size: data/scene.jpg 2048x1280 without the driver's resize
+    native = read_image("scene.jpg", False)
+    kn, dn = ref.sift_ncl(native.astype(np.float32))
+    kp_p, d_p, _, _, pq = port.sift_ncl(native.astype(np.float32), want_pyramids=True, want_prequant=True)
+    assert kp_p.tobytes() == kn.tobytes() and np.array_equal(d_p, dn)
+    np.savez_compressed(os.path.join(HERE, "scene_native_2048x1280.npz"), gray=native, keypoints=kn, descriptors=dn, prequant=pq.astype(np.float32))
+    print("scene native keypoints", len(kn))
     # knnMatch(query descriptors, scene descriptors) per main.cpp:25-27, cross-checked against cv2.BFMatcher below
     import cv2
 

@@ -63,16 +63,26 @@ def test_descriptor_stage_on_oracle_inputs(sift, oracle, synth, w, h, seed):
     assert np.allclose(np.linalg.norm(desc, axis=1), 1.0, atol=1e-5)
 
 
-def _end_to_end(sift, img, okp, odesc, opq, min_frac):
+# Descriptor gates for the default (separable-blur) pipeline, whole path.  North star: L2 <= 1e-3.  The reference quantises to uchar
+# inside the float pipeline (src/sift.cpp:709), so the ~1e-4 rounding difference between the separable blur and the reference's
+# 1369-term sequential sum flips one +-1 LSB in a few per cent of rows, and one flip moves a component by >= 1.2e-3.
+# Gates: (a) the fraction of rows within 1e-3 may not fall below the observed floor (MIN_FRAC: regressions trip), (b) EVERY row
+# beyond 1e-3 must be an explained flip -- all differing quantised integers differ by exactly 1 and the reference's pre-quantisation
+# value sat within parity.QUANT_EDGE of a rounding boundary -- i.e. unexplained == 0, with the reference's own pre-quantisation
+# vectors (fixtures *_prequant.npz, legitimate because the C port is bit-identical to oracle/_ref on those images).
+MIN_FRAC = 0.93
+
+
+def _end_to_end(sift, img, okp, odesc, opq, min_frac=MIN_FRAC):
+    assert opq is not None, "every end-to-end check classifies the rows beyond 1e-3: pre-quantisation vectors are mandatory"
     kp, desc = sift.detect_describe(img)
     pairs = parity.match_keypoints(kp, okp)
     rec, prec = parity.recall_precision(pairs, len(kp), len(okp))
     assert rec >= 0.99 and prec >= 0.99, (rec, prec, len(kp), len(okp))
     pi = np.array([p[0] for p in pairs]); pj = np.array([p[1] for p in pairs])
-    frac, explained, unexplained, mx = parity.descriptor_report(desc[pi], odesc[pj], None if opq is None else opq[pj])
+    frac, explained, unexplained, mx = parity.descriptor_report(desc[pi], odesc[pj], opq[pj])
     assert frac >= min_frac, (frac, explained, unexplained, mx)
-    if opq is not None:
-        assert unexplained <= max(1, len(pairs) // 200), (frac, explained, unexplained, mx)
+    assert unexplained == 0, (frac, explained, unexplained, mx)
     # output order = reference scan order (src/sift.cpp:556-557,487,491,525): matched pairs are index-aligned
     if len(kp) == len(okp) and len(pairs) == len(kp):
         assert all(i == j for i, j, _, _ in pairs)
@@ -82,25 +92,31 @@ def _end_to_end(sift, img, okp, odesc, opq, min_frac):
 @pytest.mark.parametrize("w,h,seed", SIZES)
 def test_end_to_end_vs_oracle(sift, oracle, synth, w, h, seed):
     """SIFT_NCL (src/sift.cpp:59-91) end to end.  Keypoints: recall/precision >= 0.99 at <= 0.01 px, <= 1 deg.
-    Descriptors: >= 85 % within 1e-3 outright (the blur's rounding differs from the reference's, so ~3-7 % of rows catch a
-    quantisation flip), the rest explained flips."""
+    Descriptors: >= MIN_FRAC within 1e-3 outright, every other row an explained +-1 LSB quantisation flip (unexplained == 0)."""
     img = synth.recipe_s(w, h, seed=seed, blobs_per_1080p=12000)
     okp, odesc, _, _, opq = _oracle_all(oracle, img)
-    _end_to_end(sift, img, okp, odesc, opq, 0.85)
+    _end_to_end(sift, img, okp, odesc, opq)
 
 
 def test_scene_960_against_reference_fixture(sift, golden):
     """BASELINE config 1: data/scene.jpg as src/main.cpp feeds it; expected values from the UNMODIFIED reference."""
     z = golden("scene_960")
-    kp, _ = _end_to_end(sift, z["gray"].astype(np.float32), z["keypoints"], z["descriptors"], None, 0.90)
+    kp, _ = _end_to_end(sift, z["gray"].astype(np.float32), z["keypoints"], z["descriptors"], golden("scene_960_prequant")["prequant"])
     assert abs(len(kp) - 486) <= 5
+
+
+def test_scene_native_against_reference_fixture(sift, golden):
+    """BASELINE config 1 at native size: data/scene.jpg 2048x1280 without the driver's resize; unmodified-reference outputs."""
+    z = golden("scene_native_2048x1280")
+    kp, _ = _end_to_end(sift, z["gray"].astype(np.float32), z["keypoints"], z["descriptors"], z["prequant"])
+    assert abs(len(kp) - 1364) <= 10
 
 
 def test_query_2448_against_reference_fixture(sift, golden):
     """BASELINE config 5 input: data/query.jpg native 2448x2448; keypoints/descriptors from the unmodified reference."""
     q = golden("query_2448")["gray"].astype(np.float32)
     z = golden("match_query_scene")
-    _end_to_end(sift, q, z["query_kp"], z["query_desc"], None, 0.90)
+    _end_to_end(sift, q, z["query_kp"], z["query_desc"], golden("query_2448_prequant")["prequant"])
 
 
 @pytest.mark.parametrize("name", ["synth_160x120", "synth_odd_211x173"])
@@ -153,7 +169,8 @@ def test_matcher_identical_indices(sift, pkg, oracle, golden):
 
 def test_tensor_core_matcher_identical_indices(sift, pkg, oracle, golden):
     """tcgen05 L2 matcher (match_tc.cu: split-bf16 MMAs -> per train split the {min, second min} of the 4 best 32-row chunks ->
-    exact fp64 re-rank of the entries whose error interval can still reach the top two): indices,
+    exact fp64 re-rank of the entries whose error interval can still reach the top two; exhaustive exact match of any query
+    whose shortlist is not provably complete): indices,
     distances and ratio flags identical to the fixture, to the exact kernel and to the oracle -- ragged tiles, duplicates
     (ties -> lowest train index), near-duplicates inside the bf16 error band, several train splits."""
     z = golden("match_query_scene")
@@ -175,12 +192,10 @@ def test_tensor_core_matcher_identical_indices(sift, pkg, oracle, golden):
         gi, gd, gg = sift.match_knn2(q, t, pkg.NORM_L2, 0.86, tensor_cores=True)
         ei, ed, eg = sift.match_knn2(q, t, pkg.NORM_L2, 0.86)
         oi, od, og = oracle.match_knn2(q, t, pkg.NORM_L2, 0.86)
-        if nt >= 100:  # six rows within the bf16-split error of each other: the documented limit of the shortlist; exclude that query
-            keep = np.ones(nq, bool); keep[2] = False
-        else:
-            keep = np.ones(nq, bool)
-        assert np.array_equal(gi[keep], ei[keep]) and np.array_equal(gd[keep], ed[keep]) and np.array_equal(gg[keep], eg[keep])
-        assert np.array_equal(gi[keep], oi[keep]) and np.array_equal(gg[keep], og[keep])
+        # t[60:66]: six rows within the bf16-split error of each other -- more than a chunk's shortlist holds; the matcher detects the
+        # incomplete shortlist and matches that query exhaustively, so there is no carve-out: every query must agree
+        assert np.array_equal(gi, ei) and np.array_equal(gd, ed) and np.array_equal(gg, eg)
+        assert np.array_equal(gi, oi) and np.array_equal(gg, og)
     # other value ranges: raw (unnormalised) SIFT-like integers 0..255, signed data, tiny magnitudes, zero rows -- the error bound and
     # the integer sort keys of the tensor path scale with |q|^2 + |t|^2, not with an absolute constant
     for make in (lambda n: rng.integers(0, 256, size=(n, 128)).astype(np.float32),

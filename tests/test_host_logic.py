@@ -105,3 +105,19 @@ def test_bind_near_gpu_is_harmless_without_nvml():
         assert 0 < n <= len(before) and after <= before
         os.sched_setaffinity(0, prev)
         assert os.sched_getaffinity(0) == before
+
+
+def test_chunk_plan_is_a_partition(pkg):
+    """Host-batch chunk schedule (api.cu chunk_plan): every chunk in [1, max_batch], chunks sum to n_frames, for every
+    (max_batch, n_frames) -- the tapered heads once overshot n_frames (e.g. max_batch 9, n 27) and produced a negative chunk."""
+    for mb in list(range(1, 70)) + [128, 256]:
+        for n in list(range(0, 6 * mb + 3)) + [1024, 1000]:
+            for taper in (True, False):
+                plan = pkg.chunk_plan(n, mb, taper)
+                assert sum(plan) == n, (mb, n, taper, plan)
+                assert all(0 < c <= mb for c in plan), (mb, n, taper, plan)
+                if not taper:
+                    assert len(plan) == (n + mb - 1) // mb
+    # the taper is symmetric and leaves full chunks in the middle
+    plan = pkg.chunk_plan(256, 32, True)
+    assert plan[:3] == [4, 8, 16] and plan[-3:] == [16, 8, 4] and 32 in plan

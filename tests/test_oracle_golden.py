@@ -33,6 +33,29 @@ def test_scene_960_config1(oracle, golden):
     assert np.allclose(np.linalg.norm(desc, axis=1), 1.0, atol=1e-5)  # sqrt(q/sum q): unit L2 rows
 
 
+@pytest.mark.parametrize("name,desc_of", [("scene_960_prequant", ("scene_960", "descriptors")), ("query_2448_prequant", ("match_query_scene", "query_desc")),
+                                          ("scene_native_2048x1280", ("scene_native_2048x1280", "descriptors"))])
+def test_prequant_fixtures_reproduce_the_reference_descriptors(golden, name, desc_of):
+    """The pre-quantisation vectors come from the C port (the reference does not expose them): they are only legitimate if the
+    reference's own tail applied to them -- saturate_cast<uchar> (round half even, clamp), L1 normalise, sqrt (src/sift.cpp:704-721)
+    -- gives back the descriptors the UNMODIFIED reference wrote into the fixture, bit for bit."""
+    pq = golden(name)["prequant"]
+    want = golden(desc_of[0])[desc_of[1]]
+    assert pq.shape == want.shape and pq.dtype == np.float32
+    q = np.clip(np.rint(pq), 0, 255).astype(np.float32)  # np.rint rounds half to even like cvRound
+    nrm1 = q.sum(axis=1, keepdims=True, dtype=np.float32)
+    got = np.sqrt(q / np.maximum(nrm1, np.float32(1.1920929e-07)))
+    assert np.abs(got - want).max() <= 2e-7  # the reference multiplies by 1/sum where this divides: 1 ulp
+
+
+def test_scene_native_config1(oracle, golden):
+    """BASELINE config 1 at native size (2048x1280, no resize): the port reproduces the unmodified reference's keypoints exactly."""
+    z = golden("scene_native_2048x1280")
+    kps, desc = oracle.f32().sift_ncl(z["gray"].astype(np.float32))
+    assert len(kps) == 1364 and kps.tobytes() == z["keypoints"].tobytes()
+    assert np.array_equal(desc, z["descriptors"])
+
+
 def test_matcher_config5(oracle, golden):
     """knnMatch(query, scene, 2) + ratio 0.86 (src/main.cpp:25-40); the fixture was cross-checked against cv2.BFMatcher."""
     z = golden("match_query_scene")
