@@ -14,7 +14,7 @@ independent, so ranks shard them with no collective on the data path (weak scali
   roofline algorithmic HBM bytes / CUDA-event time for the kernel with the largest share of the step, against
            MEASURED_PEAKS.json (per-kernel table under roofline_by_kernel; whole-path figure under roofline_pipeline)
   cpu_baseline   the reference's CPU path timed on this box (N=1, rank 0): oracle/_ref = the unmodified src/sift.cpp
-           built against oracle/cvshim (kind "reference"), else the C oracle port
+           built against third_party/cvshim (kind "reference"), else the C oracle port
 `--impl reference` times that CPU path alone and prints the same JSON shape.
 """
 from __future__ import annotations
@@ -179,7 +179,7 @@ def cpu_reference_run(steps: int, warmup: int, budget_s: float):
         cores = impl.omp_max_threads()
         full_s = 21.0  # ~10 us per pixel on a 2-3 GHz core (direct 2-D blur, src/sift.cpp:137-149)
         run = lambda img: impl.sift_ncl(img)
-        how = "oracle/_ref: unmodified src/sift.cpp compiled against oracle/cvshim; pyramid+detection single-threaded, calDescriptor OpenMP"
+        how = "oracle/_ref: unmodified src/sift.cpp compiled against third_party/cvshim; pyramid+detection single-threaded, calDescriptor OpenMP"
     else:
         kind, impl = "port", O.f32()
         cores = os.cpu_count() or 1

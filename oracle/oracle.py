@@ -1,5 +1,5 @@
 """ctypes access to the CPU oracle (oracle/liboracle.so) and, when built, to oracle/_ref/libsift_ref.so
-(the unmodified reference src/sift.cpp compiled against oracle/cvshim).
+(the unmodified reference src/sift.cpp compiled against third_party/cvshim).
 
 TEST INFRASTRUCTURE ONLY: importable from tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
 --impl reference legs.  The product package never imports this module.

@@ -1,7 +1,7 @@
 /*
  * oracle_prims.h -- restatement of the OpenCV 4.0.x primitives the reference's hot path calls.
  *
- * TEST INFRASTRUCTURE ONLY (used by the oracle and by oracle/cvshim, never by the product).
+ * TEST INFRASTRUCTURE ONLY (used by the oracle and by third_party/cvshim, never by the product).
  *
  * OpenCV is a third-party dependency of the reference that is NOT under /root/reference: the makefile
  * links /usr/local/lib/libopencv_*.so.4.0 (makefile:28-29) and there is no lockfile, so the pin is

@@ -1,8 +1,8 @@
 // api.cu -- the C ABI of include/sift_b200.h: handle, workspace layout, stage orchestration.
 //
 // One handle = one device workspace for up to max_batch frames of up to max_rows x max_cols.  The whole path
-// (base blur -> 5 x octave blur+DoG -> extrema+refine -> orientation -> order+scan -> descriptors) is ten
-// kernel launches per chunk of max_batch frames, all asynchronous on the caller's stream, no host sync and no
+// (base blur -> 5 x octave blur+DoG -> gradient maps -> extrema+refine -> orientation -> order+scan -> descriptor prep + descriptors)
+// is thirteen kernel launches per chunk of max_batch frames, all asynchronous on the caller's stream, no host sync and no
 // CPU fallback anywhere: if CUDA is unavailable every entry point returns SIFT_B200_ERR_CUDA.
 #include <math.h>
 #include <stdio.h>
@@ -211,12 +211,14 @@ int alloc_detectbuf(DetectBuf& db, size_t F, int cap_r) {
     CUDA_TRY(cudaMalloc((void**)&db.order, F * C * sizeof(int)));
     CUDA_TRY(cudaMalloc((void**)&db.kp_offset, F * C * sizeof(int)));
     CUDA_TRY(cudaMalloc((void**)&db.sort_tmp, F * (size_t)db.cap_r_pow2 * sizeof(unsigned long long)));
+    CUDA_TRY(cudaMalloc((void**)&db.dparams, F * C * sizeof(DescParams)));
+    CUDA_TRY(cudaMalloc((void**)&db.n_kp, F * sizeof(int)));
     return SIFT_B200_OK;
 }
 
 void free_detectbuf(DetectBuf& db) {
     cudaFree(db.cand); cudaFree(db.n_cand); cudaFree(db.refined); cudaFree(db.n_refined); cudaFree(db.angles); cudaFree(db.n_peaks);
-    cudaFree(db.order); cudaFree(db.kp_offset); cudaFree(db.sort_tmp);
+    cudaFree(db.order); cudaFree(db.kp_offset); cudaFree(db.sort_tmp); cudaFree(db.dparams); cudaFree(db.n_kp);
     db = DetectBuf{};
 }
 
@@ -319,6 +321,9 @@ struct Event {
 
 extern "C" {
 
+static int create_impl(SiftB200* h);
+int sift_b200_destroy(SiftB200* h);
+
 const char* sift_b200_last_error(void) { return g_err.c_str(); }
 const char* sift_b200_version(void) { return "sift_b200 0.1 (sm_100a)"; }
 
@@ -331,7 +336,20 @@ int sift_b200_create(SiftB200** out, int max_rows, int max_cols, int max_batch, 
     CUDA_TRY(cudaSetDevice(device));
     SiftB200* h = new SiftB200();
     h->device = device; h->max_rows = max_rows; h->max_cols = max_cols; h->max_batch = max_batch; h->cap_kp = max_kp_per_frame;
+    *out = nullptr;
+    const int rc = create_impl(h);
+    if (rc != SIFT_B200_OK) {  // a partially built handle is torn down here: the caller gets no handle and nothing leaks
+        const std::string keep = g_err;
+        sift_b200_destroy(h);
+        g_err = keep;
+        return rc;
+    }
     *out = h;
+    return SIFT_B200_OK;
+}
+
+static int create_impl(SiftB200* h) {
+    const int max_rows = h->max_rows, max_cols = h->max_cols, max_batch = h->max_batch, max_kp_per_frame = h->cap_kp;
     CUDA_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     h->ws_floats = frame_floats(max_rows, max_cols, 5, 11) * max_batch;  // G0..G2, D0..D3, 2 x float2 gradient maps
     CUDA_TRY(cudaMalloc((void**)&h->ws, h->ws_floats * sizeof(float)));
@@ -455,8 +473,25 @@ static std::vector<int> chunk_plan(int n_frames, int max_batch, bool taper) {
 // Host batch, software-pipelined over the chunks of chunk_plan(): the H2D of chunk k+1 (stream s_in, three input buffers) and the
 // exact-size D2H of chunk k-1 (stream s_out) overlap the kernels of chunk k, which alternate between the two compute lanes.  The
 // host only ever waits for the tiny counts copy of the PREVIOUS chunk, after the next chunk's copy and kernels have been queued.
+static int batch_host_run(SiftB200* h, const void* imgs_v, int elem, int n_frames, int rows, int cols, SiftKeypoint* kp_out, float* desc_out,
+                          int* counts_out, int cap);
+
+// On a failure in the middle of a batch, copies into the caller's buffers may still be queued: drain every stream the pipeline uses
+// before the error is returned, so nothing writes into caller memory after the call.
 static int batch_host_impl(SiftB200* h, const void* imgs_v, int elem, int n_frames, int rows, int cols, SiftKeypoint* kp_out, float* desc_out,
                            int* counts_out, int cap) {
+    const int rc = batch_host_run(h, imgs_v, elem, n_frames, rows, cols, kp_out, desc_out, counts_out, cap);
+    if (rc != SIFT_B200_OK && rc != SIFT_B200_ERR_CAPACITY && h) {
+        const std::string keep = g_err;
+        for (cudaStream_t st : {h->s_in, h->s_out, h->stream, h->stream2})
+            if (st) cudaStreamSynchronize(st);
+        g_err = keep;
+    }
+    return rc;
+}
+
+static int batch_host_run(SiftB200* h, const void* imgs_v, int elem, int n_frames, int rows, int cols, SiftKeypoint* kp_out, float* desc_out,
+                          int* counts_out, int cap) {
     const unsigned char* imgs = static_cast<const unsigned char*>(imgs_v);  // elem = 4 (float32 frames) or 1 (uint8 frames)
     int rc = check_dims(h, rows, cols);
     if (rc) return rc;
@@ -585,16 +620,16 @@ int sift_b200_detect_describe_up2(SiftB200* h, const float* img, int rows, int c
     if (!img || !kp_out || !desc_out || !n_out) return fail(SIFT_B200_ERR_ARG, "null buffer");
     CUDA_TRY(cudaSetDevice(h->device));
     if ((rc = ensure_staging(h))) return rc;
-    float* d_src = nullptr;
-    CUDA_TRY(cudaMalloc((void**)&d_src, (size_t)rows * cols * 4));
+    DevMem m_src;  // freed on every exit path (after the stream has been synchronised, or on an error before any use)
+    CUDA_TRY(m_src.alloc((size_t)rows * cols * 4));
+    float* d_src = m_src.as<float>();
     CUDA_TRY(cudaMemcpyAsync(d_src, img, (size_t)rows * cols * 4, cudaMemcpyHostToDevice, h->stream));
     h->launches += launch_upsample2x(d_src, h->d_img, rows, cols, 1, h->stream);
     if (upsampled_out) CUDA_TRY(cudaMemcpyAsync(upsampled_out, h->d_img, (size_t)rows * cols * 16, cudaMemcpyDeviceToHost, h->stream));
     rc = run_pipeline(h, h->d_img, nullptr, 1, 2 * rows, 2 * cols, h->d_kp, h->d_desc, h->d_counts, cap, h->stream);
-    if (rc) { cudaFree(d_src); return rc; }
+    if (rc) { cudaStreamSynchronize(h->stream); return rc; }
     CUDA_TRY(cudaMemcpyAsync(h->h_counts, h->d_counts, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
-    cudaFree(d_src);
     int n = h->h_counts[0];
     *n_out = n;
     int status = SIFT_B200_OK;
@@ -629,11 +664,12 @@ static int blur_any(SiftB200* h, const float* src, int rows, int cols, double si
         for (int i = -radius; i <= radius; ++i) taps[i + radius] = (float)(1. / sqrt(2 * PI * sigma_d * sigma_d) * exp(-((double)i * i) * 1. / (2 * sigma_d * sigma_d)));
         hi = radius - 1;
     }
-    float *d_src = nullptr, *d_dst = nullptr, *d_taps = nullptr;
     const size_t n = (size_t)rows * cols;
-    CUDA_TRY(cudaMalloc((void**)&d_src, n * 4));
-    CUDA_TRY(cudaMalloc((void**)&d_dst, n * 4));
-    CUDA_TRY(cudaMalloc((void**)&d_taps, taps.size() * 4));
+    DevMem m_src, m_dst, m_taps;  // freed on every exit path
+    CUDA_TRY(m_src.alloc(n * 4));
+    CUDA_TRY(m_dst.alloc(n * 4));
+    CUDA_TRY(m_taps.alloc(taps.size() * 4));
+    float *d_src = m_src.as<float>(), *d_dst = m_dst.as<float>(), *d_taps = m_taps.as<float>();
     CUDA_TRY(cudaMemcpyAsync(d_src, src, n * 4, cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(cudaMemcpyAsync(d_taps, taps.data(), taps.size() * 4, cudaMemcpyHostToDevice, h->stream));
     const int nl = launch_generic_blur(d_src, d_dst, rows, cols, d_taps, radius, hi, h->stream);
@@ -641,7 +677,6 @@ static int blur_any(SiftB200* h, const float* src, int rows, int cols, double si
     h->launches += nl;
     CUDA_TRY(cudaMemcpyAsync(dst, d_dst, n * 4, cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
-    cudaFree(d_src); cudaFree(d_dst); cudaFree(d_taps);
     CUDA_TRY(cudaGetLastError());
     return SIFT_B200_OK;
 }
@@ -728,19 +763,20 @@ int sift_b200_cal_descriptor(SiftB200* h, const float* gpyr, int rows, int cols,
     PyrView pv;
     if ((rc = make_view(h->ws_full, rows, cols, n_octaves, 1, true, &pv))) return fail(rc, "make_view");
     if ((rc = copy_levels(pv, true, 5, const_cast<float*>(gpyr), true, h->stream))) return rc;
-    SiftKeypoint* d_k = nullptr; float* d_d = nullptr; int* d_err = nullptr;
-    CUDA_TRY(cudaMalloc((void**)&d_k, (size_t)n * sizeof(SiftKeypoint)));
-    CUDA_TRY(cudaMalloc((void**)&d_d, (size_t)n * 128 * 4));
-    CUDA_TRY(cudaMalloc((void**)&d_err, 4));
+    DevMem m_k, m_d, m_err, m_par;  // freed on every exit path
+    CUDA_TRY(m_k.alloc((size_t)n * sizeof(SiftKeypoint)));
+    CUDA_TRY(m_d.alloc((size_t)n * 128 * 4));
+    CUDA_TRY(m_err.alloc(4));
+    CUDA_TRY(m_par.alloc((size_t)n * sizeof(DescParams)));
+    SiftKeypoint* d_k = m_k.as<SiftKeypoint>(); float* d_d = m_d.as<float>(); int* d_err = m_err.as<int>();
     CUDA_TRY(cudaMemsetAsync(d_err, 0, 4, h->stream));
     CUDA_TRY(cudaMemcpyAsync(d_k, kps, (size_t)n * sizeof(SiftKeypoint), cudaMemcpyHostToDevice, h->stream));
     h->launches += launch_gradient(pv, 1, h->stream);
-    h->launches += launch_describe_given(pv, d_k, n, d_d, first_octave, d_err, h->stream);
+    h->launches += launch_describe_given(pv, d_k, n, d_d, first_octave, d_err, m_par.as<DescParams>(), h->stream);
     int err = 0;
     CUDA_TRY(cudaMemcpyAsync(desc, d_d, (size_t)n * 128 * 4, cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(cudaMemcpyAsync(&err, d_err, 4, cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
-    cudaFree(d_k); cudaFree(d_d); cudaFree(d_err);
     CUDA_TRY(cudaGetLastError());
     if (err) return fail(SIFT_B200_ERR_ASSERT, "octave >= firstOctave && layer <= nOctaveLayers+2 (src/sift.cpp:744)");
     return SIFT_B200_OK;

@@ -6,26 +6,30 @@
 //
 // The reference scatters every window sample into a (4+2)x(4+2)x(8+2) histogram.  A scatter into one shared histogram
 // needs shared-memory float atomics, which on sm_100a are CAS loops (ATOMS.CAST.SPIN) that serialise badly because
-// neighbouring samples hit the same bins.  This kernel is atomics-free and deterministic, one CTA of five warps per
-// keypoint, one pass ("slab warps"):
-//   - the window is cut into the five unit slabs of the row coordinate, r0 <= rbin < r0+1 for r0 = -1..3; warp s owns slab
-//     r0 = s-1, so every sample is evaluated exactly once, floor(rbin) is a warp constant (no floor, no per-sample cell-row
-//     logic) and the two cell-rows a slab votes into (r0, r0+1) are static: the border warps (r0 = -1, 3) skip the half of the
-//     votes that falls outside the 4x4 grid with a warp-uniform branch instead of sending them to trash bins;
-//   - a group of GL lanes (GL = 4..32, chosen per keypoint from the mean run length of a slab row) walks a window row's j-interval
-//     of the slab (two slab inequalities rounded outwards by 1e-3 px; the reference's own float test decides membership), one
-//     sample per lane per step, the gradient-map load of the step three ahead already in flight;
-//   - the Gaussian weight is separable in window coordinates (rotation preserves i^2+j^2): exp(-(i^2+j^2)/(8 hw^2)) =
-//     wrow[i] * wcol[j], two small per-keypoint tables instead of an expf per sample (|relative difference| to the reference's
-//     exp of the rotated, rounded coordinates ~1e-7);
-//   - the trilinear votes (reference operation order, :656-672) go to THREAD-PRIVATE histograms [2 cell-rows][6 cells][9 bins] in
-//     shared memory (layout [bin][thread]: conflict-free plain read-modify-write, one address register + immediates); the two
-//     extra cells (c0 = -1 and c0+1 = 4) absorb the out-of-grid column votes without any select;
-//   - tail: column sums over the 32 private copies of each warp (rotated, conflict-free), slab pairs added per cell-row,
-//     circular bin fold, then L2 -> clamp 0.2 -> x512 -> uchar (round half even) -> L1 -> sqrt with block reductions.
+// neighbouring samples hit the same bins.  This path is atomics-free, barrier-free and deterministic:
+//
+//   describe_prep_kernel   thread per output keypoint: everything that depends on the keypoint alone (rounded centre, rotation
+//                          scaled by the cell width, weight exponent, clipped window, slab-interval constants) is computed ONCE
+//                          into a 64-byte DescParams record, and the 28-byte keypoint record is written.
+//   describe_kernel        ONE WARP per keypoint (four independent warps per CTA, no __syncthreads anywhere).  The window is cut
+//                          into the five unit slabs of the row coordinate, r0 <= rbin < r0+1 for r0 = -1..3, processed one after
+//                          the other:
+//     - floor(rbin) is a constant of the slab: no floor, no per-sample cell-row logic, every sample is evaluated exactly once, and
+//       the border slabs (r0 = -1, 3) skip the half of the votes that falls outside the 4x4 grid with a warp-uniform branch;
+//     - the slab's samples are enumerated as a compact list of 4-pixel chunks of window rows (row intervals from two slab
+//       inequalities rounded outwards by 1e-3 px; the reference's own float test decides membership): step k gives chunk 8k+g
+//       to lane group g, so all 32 lanes stay busy whatever the rotation, consecutive groups read consecutive pixels, and the
+//       gradient-map load of the step three ahead is already in flight;
+//     - the Gaussian weight is separable in window coordinates (rotation preserves i^2+j^2): exp(-(i^2+j^2)/(8 hw^2)) =
+//       wrow[i] * wcol[j], two small per-keypoint tables instead of an expf per sample (|relative difference| to the reference's
+//       exp of the rotated, rounded coordinates ~1e-7);
+//     - the trilinear votes (reference operation order, :656-672) go to LANE-PRIVATE histograms in shared memory, layout
+//       [cell-row buffer 0/1][6 cells][9 bins][32 lanes]: conflict-free plain read-modify-write, one address computation + immediates;
+//       the two extra cells (c0 = -1 and c0+1 = 4) absorb the out-of-grid column votes without any select.  Slab r0 votes into
+//       cell-rows r0 and r0+1, so the two buffers roll: after slab r0 cell-row r0 is complete, its 36 bins are summed over the 32
+//       lanes (rotated 16-byte reads, conflict-free), the circular bin is folded, and lane l keeps output element (r0, l) in a register;
+//     - tail in registers + shuffles: L2 -> clamp 0.2 -> x512 -> uchar (round half even) -> L1 -> sqrt.
 // Only the inner 4x4 cells are kept by the reference (:676-684), so the border cells are never formed.
-#include <type_traits>
-
 #include "sift_internal.cuh"
 
 namespace siftb200 {
@@ -33,31 +37,54 @@ namespace {
 
 constexpr int DW = 4, DB = 8;  // SIFT_DESCR_WIDTH, SIFT_DESCR_HIST_BINS (src/sift.cpp:12,15)
 constexpr int NSLAB = DW + 1;  // floor(rbin) in -1..3
-constexpr int DT = NSLAB * 32; // threads per CTA: one warp per slab
-constexpr int PC = DW + 2;     // private cells per cell-row: c0+1 in 0..5 (cells -1 and 4 are scratch)
-constexpr int PRIV_BINS = 2 * PC * (DB + 1);   // private histogram of one thread: [2 cell-rows][6 cells][9 bins]
-constexpr int PRIV_FLOATS = PRIV_BINS * DT;
-constexpr int NB = 84;                         // window rows per band (tables of one band live in shared memory); radius <= 40 => one band
-constexpr int WCOL = 96;                       // columns per block (column-weight table); radius <= 40 => one block
-constexpr int NSUM = NSLAB * 2 * DW * (DB + 1);  // column sums of the tail: [slab][cell-row][4 cells][9 bins]
-constexpr int CTAS_PER_SM = 3;
-// shared memory: private histograms | per-(slab,row) j-intervals (int2) | per-row {i*sin, i*cos, wrow, -} | wcol | reduction scratch.
-// The tail's column sums alias the interval table.
-constexpr int TAB_BYTES = NSLAB * NB * 8, ROW_BYTES = NB * 16;
-constexpr int DESC_SMEM_BYTES = PRIV_FLOATS * 4 + TAB_BYTES + ROW_BYTES + WCOL * 4 + 32;
-static_assert(NSUM * 4 <= TAB_BYTES, "tail sums alias the interval table");
+// Shape of a lane's private histogram (tuning knobs; the smaller it is, the more warps an SM holds -- the kernel is latency bound):
+//   DESC_CELLS 6: cells c0+1 in 0..5, cells 0 and 5 are scratch for the out-of-grid column votes (no extra instruction)
+//              5: one scratch cell (index 0) shared by c0 = -1 and c0+1 = 4 (one select)
+//              4: no scratch: out-of-grid votes are clamped into the grid and their stores predicated off
+//   DESC_BINS  9: bin o0+1 = 8 is folded onto bin 0 in the tail;  8: (o0+1) & 7 wraps at vote time
+#ifndef DESC_CELLS
+#define DESC_CELLS 4
+#endif
+#ifndef DESC_BINS
+#define DESC_BINS 9
+#endif
+constexpr int PC = DESC_CELLS;  // private cells per cell-row
+constexpr int PB = DESC_BINS;   // private bins per cell
+constexpr int C1 = PC == 4 ? 0 : 1;            // private index of grid cell 0
+constexpr int ROWBUF = PC * PB * 32;           // floats of one cell-row buffer: [cells][bins][32 lanes]
+constexpr int NB = 84;         // window rows per block (row tables live in shared memory); radius <= 40 => one block
+constexpr int WCOL = 96;       // window columns per block (column-weight table)
+constexpr int NCHUNK = 248;    // chunk-list capacity per pass (a pipeline slab needs <= 244)
+constexpr int NPAD = 8;        // dummy chunks behind the list: round up to a whole step
+// shared memory per warp (floats): private histograms | rowA float4[NB+1] {i*sin, i*cos, wrow, row offset} (+1 dummy row) | wcol[WCOL] | chunk list
+constexpr int WARP_FLOATS = 2 * ROWBUF + 4 * (NB + 1) + WCOL + NCHUNK + NPAD;
+static_assert(WARP_FLOATS % 4 == 0, "16-byte alignment of every warp's region");
+#ifndef DESC_RING
+#define DESC_RING 3
+#endif
+#ifndef DESC_ROLES
+#define DESC_ROLES 1  // 1: the walk is instantiated per slab role (border slabs skip half the votes); 0: one instantiation
+#endif
+constexpr int RING = DESC_RING;  // gradient-map loads in flight per lane
+#ifndef DESC_WARPS_PER_CTA
+#define DESC_WARPS_PER_CTA 2
+#endif
+constexpr int DESC_WARPS = DESC_WARPS_PER_CTA;  // independent warps per CTA
+constexpr int DESC_SMEM_BYTES = DESC_WARPS * WARP_FLOATS * 4;
+// register budget: the launch bound asks for one CTA less than shared memory admits when that avoids spills (DESC_MIN_CTAS)
+constexpr int CTAS_PER_SM = (227 * 1024) / (DESC_SMEM_BYTES + 1024) < 32 / DESC_WARPS ? (227 * 1024) / (DESC_SMEM_BYTES + 1024) : 32 / DESC_WARPS;
+
+#ifndef DESC_MIN_CTAS
+#define DESC_MIN_CTAS CTAS_PER_SM
+#endif
 
 __device__ __forceinline__ int cv_round(float v) { return __float2int_rn(v); }
 __device__ __forceinline__ int cv_floor(float v) { return __float2int_rd(v); }
 
-// sum over the CTA (5 warps); every thread gets the result.  `red` = 8 floats of shared scratch.
-__device__ __forceinline__ float block_sum(float v, float* red, int tid) {
+__device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
-    __syncthreads();
-    if ((tid & 31) == 0) red[tid >> 5] = v;
-    __syncthreads();
-    return ((red[0] + red[1]) + (red[2] + red[3])) + red[4];
+    return v;
 }
 
 // window radius of calcSIFTDescriptor (:587-590)
@@ -68,11 +95,37 @@ __device__ __forceinline__ int descr_radius(float scl, int rows, int cols) {
     return min(radius, diag);
 }
 
-// j-interval of {lo_v <= j*k + off <= hi_v} widened by a margin that covers the rounding of this very computation, intersected into
-// [lo, hi]; false when the row misses the slab.  `flat`: k is so small that j*k moves by < 0.05 over the window: the row is inside or
-// outside as a whole (tested with that slack).  The exact per-sample test decides membership; this only has to be a superset.
-__device__ __forceinline__ bool slab(float k, float inv_k, float margin, bool flat, float off, float lo_v, float hi_v, float& lo, float& hi) {
-    if (!flat) {
+// Everything calcSIFTDescriptor derives from the keypoint alone (:579-612), for one keypoint of level (octave, layer).
+__device__ DescParams make_params(int rows, int cols, int level, float ptx, float pty, float ori, float scl) {
+    DescParams P;
+    P.px = cv_round(ptx); P.py = cv_round(pty);
+    const float cos_u = cosf(ori * (float)(3.1415926535897932384626433832795 / 180));
+    const float sin_u = sinf(ori * (float)(3.1415926535897932384626433832795 / 180));
+    const float hist_width = 3.f * scl;
+    const int radius = descr_radius(scl, rows, cols);
+    P.cos_t = cos_u / hist_width;
+    P.sin_t = sin_u / hist_width;
+    P.ori = ori;
+    // exponent of the separable weight: (c_rot^2 + r_rot^2) * (-1/8) = (i^2 + j^2) * (cos_t^2 + sin_t^2) * (-1/8)
+    P.es = (float)(-0.125 * ((double)P.cos_t * P.cos_t + (double)P.sin_t * P.sin_t));
+    P.jmin = max(-radius, 1 - P.px); P.jmax = min(radius, cols - 2 - P.px);   // 0 < c < cols-1  (:621)
+    P.imin = max(-radius, 1 - P.py); P.imax = min(radius, rows - 2 - P.py);   // 0 < r < rows-1
+    // slab-interval constants: a direction whose coefficient moves the bin coordinate by < 0.05 over the whole window is "flat"
+    // (inv = 0: rows are inside or outside as a whole); otherwise intervals are widened by a margin that covers their own rounding
+    const float wspan = (float)(radius > 1 ? radius : 1);
+    const bool flat_s = fabsf(P.sin_t) * wspan < 0.05f, flat_c = fabsf(P.cos_t) * wspan < 0.05f;
+    P.inv_s = flat_s ? 0.f : 1.f / P.sin_t;
+    P.inv_c = flat_c ? 0.f : 1.f / P.cos_t;
+    P.mar_s = 1e-3f + 4e-6f * fabsf(P.inv_s);
+    P.mar_c = 1e-3f + 4e-6f * fabsf(P.inv_c);
+    P.level = level;
+    return P;
+}
+
+// j-interval of {lo_v <= j*k + off <= hi_v} widened by `margin`, intersected into [lo, hi]; false when the row misses the slab.
+// inv_k == 0 marks a flat direction (tested with slack).  The exact per-sample test decides membership; this only has to be a superset.
+__device__ __forceinline__ bool slab(float inv_k, float margin, float off, float lo_v, float hi_v, float& lo, float& hi) {
+    if (inv_k != 0.f) {
         const float u0 = (lo_v - off) * inv_k, u1 = (hi_v - off) * inv_k;
         lo = fmaxf(lo, fminf(u0, u1) - margin);
         hi = fminf(hi, fmaxf(u0, u1) + margin);
@@ -81,228 +134,276 @@ __device__ __forceinline__ bool slab(float k, float inv_k, float margin, bool fl
     return off > lo_v - 0.06f && off < hi_v + 0.06f;
 }
 
-// calcSIFTDescriptor, src/sift.cpp:579-722, for one keypoint by one CTA.  dst: 128 floats in global memory.
-// mo: the level's gradient map {Mag, Ori} (detect.cu gradient_kernel) -- the values the reference computes per sample (:623-633).
-__device__ void calc_descriptor(const float2* __restrict__ mo, int rows, int cols, int pitch, float ptx, float pty, float ori, float scl, float gl_div,
-                                float* __restrict__ smem, float* __restrict__ dst) {
-    const int tid = threadIdx.x, lane = tid & 31, s = tid >> 5;  // s: slab, floor(rbin) = s - 1
-    const int px = cv_round(ptx), py = cv_round(pty);
-    const float cos_u = cosf(ori * (float)(3.1415926535897932384626433832795 / 180));
-    const float sin_u = sinf(ori * (float)(3.1415926535897932384626433832795 / 180));
+// One slab's walk over its chunk list.  HAS_LO / HAS_HI: cell-rows r0 and r0+1 lie inside the 4x4 grid (the border slabs carry half the
+// votes).  Step k hands chunk 8k + grp to lane group grp; the gradient-map load of step k+3 is issued before the votes of step k.
+// A stage carries the sample's bin coordinates, weight and gradient; padding chunks sit on a dummy row whose row coordinate lies
+// outside every slab, a lane past the end of its chunk gets cbin = 1e9: both are rejected by the reference's own range test (:620).
+template <bool HAS_LO, bool HAS_HI>
+__device__ __forceinline__ void walk_slab(const float2* __restrict__ mo, const float4* __restrict__ s_rowA, const float* __restrict__ s_wcol,
+                                          const int* __restrict__ s_chunk, int nsteps, int cb0, float cos_t, float sin_t, float ori, float r0f, float r1f,
+                                          float* __restrict__ priv, int grp, int gl) {
     const float bins_per_rad = DB / 360.f;
-    const float hist_width = 3.f * scl;
-    const int radius = descr_radius(scl, rows, cols);
-    const float cos_t = cos_u / hist_width;
-    const float sin_t = sin_u / hist_width;
-    // exponent of the separable weight: (c_rot^2 + r_rot^2) * (-1/8) = (i^2 + j^2) * (cos_t^2 + sin_t^2) * (-1/8)
-    const float es = (float)(-0.125 * ((double)cos_t * cos_t + (double)sin_t * sin_t));
-    float* s_priv = smem;                                              // [PRIV_BINS][DT]
-    int2* s_tab = reinterpret_cast<int2*>(smem + PRIV_FLOATS);         // [NSLAB][NB] {jlo, jhi}
-    float* s_sum = reinterpret_cast<float*>(s_tab);                    // tail only
-    float4* s_row = reinterpret_cast<float4*>(s_tab + NSLAB * NB);     // [NB] {i*sin_t, i*cos_t, wrow, -}
-    float* s_wcol = reinterpret_cast<float*>(s_row + NB);              // [WCOL] wcol[j - cb0]
-    float* s_red = s_wcol + WCOL;                                      // 8 floats
-    const int jmin = max(-radius, 1 - px), jmax = min(radius, cols - 2 - px);   // 0 < c < cols-1  (:621)
-    const int imin = max(-radius, 1 - py), imax = min(radius, rows - 2 - py);   // 0 < r < rows-1
-
-    for (int k = tid * 4; k < PRIV_FLOATS; k += DT * 4) *reinterpret_cast<float4*>(s_priv + k) = make_float4(0.f, 0.f, 0.f, 0.f);
-    // slab geometry (per keypoint): interval margins, flat-direction flags, lanes per group
-    const float wspan = (float)(radius > 1 ? radius : 1);
-    const bool flat_s = fabsf(sin_t) * wspan < 0.05f, flat_c = fabsf(cos_t) * wspan < 0.05f;
-    const float inv_s = flat_s ? 0.f : 1.f / sin_t, inv_c = flat_c ? 0.f : 1.f / cos_t;
-    const float mar_s = 1e-3f + 4e-6f * fabsf(inv_s), mar_c = 1e-3f + 4e-6f * fabsf(inv_c);
-    // mean run length of a slab row: (slab area 5 hw^2) / (rows it crosses, hw (|cos| + 5 |sin|)); lanes per group = largest power of
-    // two <= run / gl_div, in [4, 32] (longer groups: fewer 128-byte lines per gather; shorter: fewer idle lanes at row ends)
-    const float run = 5.f * hist_width / (fabsf(cos_u) + 5.f * fabsf(sin_u));
-    int glsh = 2;
-    while (glsh < 5 && (float)(2 << glsh) * gl_div <= run) ++glsh;
-    const int GL = 1 << glsh, gl = lane & (GL - 1), slot = lane >> glsh, ng = 32 >> glsh;
-    const float r0f = (float)(s - 1), r1f = (float)s;
-    float* priv = s_priv + tid;
-    // The tables are addressed relative to `priv` (an address the walk keeps in a register anyway); the opaque copy of tid keeps the
-    // compiler from folding this back to the shared-window base, which it would re-materialise (S2R + 2 ops) at every use.
-    int tid_o = tid;
-    asm volatile("" : "+r"(tid_o));
-    const float* wcol_p = priv + (PRIV_FLOATS + (TAB_BYTES + ROW_BYTES) / 4 - tid_o);       // == s_wcol
-    const int2* tab_p = reinterpret_cast<const int2*>(priv + (PRIV_FLOATS - tid_o)) + s * NB;  // == s_tab + s * NB
-    const float4* row_p = reinterpret_cast<const float4*>(priv + (PRIV_FLOATS + TAB_BYTES / 4 - tid_o));  // == s_row
-    // The window is processed in blocks of NB rows x WCOL columns so that the interval and weight tables fit shared memory whatever the
-    // keypoint size; a pipeline keypoint (radius <= 40) is one block.
-    for (int band0 = imin; band0 <= imax; band0 += NB)
-    for (int cb0 = jmin; cb0 <= jmax; cb0 += WCOL) {
-        const int nrows = min(NB, imax - band0 + 1);
-        const int cb1 = min(jmax, cb0 + WCOL - 1);
-        __syncthreads();  // previous block's walk (and the zeroing above) done before the tables are rewritten
-        for (int k = tid; k <= cb1 - cb0; k += DT) s_wcol[k] = expf((float)((cb0 + k) * (cb0 + k)) * es);
-        // per row: the column-slab interval -1 < cbin < 4 (shared by the five row slabs), then the five row-slab intervals
-        for (int r = tid; r < nrows; r += DT) {
-            const int i = band0 + r;
-            const float isin = i * sin_t, icos = i * cos_t;
-            s_row[r] = make_float4(isin, icos, expf((float)(i * i) * es), 0.f);
-            float lo0 = (float)cb0, hi0 = (float)cb1;
-            const bool ok0 = slab(cos_t, inv_c, mar_c, flat_c, -isin + 1.5f, -1.f, 4.f, lo0, hi0);
-#pragma unroll
-            for (int q = 0; q < NSLAB; ++q) {
-                float lo = lo0, hi = hi0;
-                const bool ok = ok0 && slab(sin_t, inv_s, mar_s, flat_s, icos + 1.5f, q - 1.f, (float)q, lo, hi);
-                s_tab[q * NB + r] = ok ? make_int2(max(cb0, (int)ceilf(lo)), min(cb1, (int)floorf(hi))) : make_int2(1, 0);
-            }
+    auto issue = [&](float& st_rbin, float& st_cbin, float& st_w, float2& st_mo, int k) {
+        const int e = s_chunk[k * 8 + grp];
+        const int r = e & 255, joff = (e >> 8) & 255, cnt = e >> 16, j0 = joff + cb0;  // j0: window column of the chunk's first pixel
+        const int d = min(gl, cnt - 1);  // clamped: always a pixel of the interval / a table entry
+        const float4 rv = s_rowA[r];
+        st_mo = __ldg(mo + (__float_as_int(rv.w) + j0 + d));
+        st_w = rv.z * s_wcol[joff + d];
+        const float jf = (float)(j0 + gl);
+        const float c_rot = jf * cos_t - rv.x;
+        const float r_rot = jf * sin_t + rv.y;
+        st_rbin = r_rot + DW / 2 - 0.5f;
+        const float cbin = c_rot + DW / 2 - 0.5f;
+        st_cbin = gl < cnt ? cbin : 1e9f;
+    };
+    // one step: the trilinear votes of the sample of this lane, branch-free
+    auto vote = [&](const float rbin, const float cbin, const float st_w, const float2 st_mo) {
+        // floor(rbin) == r0 (this slab); rbin == -1 exactly (rejected by the reference) votes 0
+        const bool racc = rbin >= r0f && rbin < r1f;
+        const int c0 = cv_floor(cbin);  // 1e9 saturates to INT_MAX
+        float obin = (st_mo.y - ori) * bins_per_rad;
+        const int o0 = cv_floor(obin);
+        obin -= o0;
+        // private bin addresses: cells cA (c0) and cB (c0+1), bins oA (o0) and oB (o0+1); o0 in [-8, 7]: the reference's two wrap tests == & 7
+        const int oA = (o0 & (DB - 1)) * 32;
+        const int oB = PB == 9 ? oA + 32 : ((o0 + 1) & (DB - 1)) * 32;
+        int cA, cB;
+        bool stA = true, stB = true;
+        float mag, cf;
+        if (PC == 4) {
+            // -1 < cbin < 4 (:620) <=> c0 in [-1, 3] (cbin == -1 exactly votes 0 into the grid); votes for cells outside the grid are formed
+            // on a clamped address and not stored
+            stA = (unsigned)c0 <= (unsigned)(DW - 1);
+            stB = (unsigned)(c0 + 1) <= (unsigned)(DW - 1);
+            cA = min(max(c0, 0), DW - 1) * (PB * 32);
+            cB = min(max(c0 + 1, 0), DW - 1) * (PB * 32);
+            mag = racc ? st_mo.x * st_w : 0.f;
+            cf = cbin - (float)c0;
+        } else {
+            const bool acc = racc && cbin > -1 && cbin < DW;
+            mag = acc ? st_mo.x * st_w : 0.f;
+            const int c0s = acc ? c0 : 0;
+            cf = acc ? cbin - (float)c0 : 0.f;
+            cA = (c0s + 1) * (PB * 32);
+            cB = (PC == 5 && c0s == DW - 1) ? 0 : cA + PB * 32;
         }
-        __syncthreads();
-        // first / last non-empty row of this warp's slab
-        int rlo = nrows, rhi = -1;
-        for (int rb = 0; rb < nrows; rb += 32) {
-            const int r = rb + lane;
-            bool ne = false;
-            if (r < nrows) { const int2 t = s_tab[s * NB + r]; ne = t.x <= t.y; }
-            const unsigned m = __ballot_sync(0xffffffffu, ne);
-            if (m) { rlo = min(rlo, rb + __ffs(m) - 1); rhi = rb + 31 - __clz(m); }
-        }
-        // has_lo / has_hi: cell-rows r0 and r0+1 lie inside the 4x4 grid (compile-time per warp role: border warps carry half the votes)
-        auto walk = [&](auto LO, auto HI) {
-            constexpr bool has_lo = decltype(LO)::value, has_hi = decltype(HI)::value;
-            // flattened walk: a group advances through its rows (rlo+slot, +ng, ...) one GL-sample step per iteration (one sample per
-            // lane), so the groups of a warp never wait for each other at row boundaries.
-            int r = rlo + slot - ng, jb = 1, jhi = 0;
-            const float2* rowp = mo;
-            float isin = 0.f, icos = 0.f, wrow = 0.f;
-            auto advance = [&]() -> bool {
-                jb += GL;
-                if (jb > jhi) {
-                    do {
-                        r += ng;
-                        if (r > rhi) return false;
-                        const int2 t = tab_p[r];
-                        jb = t.x; jhi = t.y;
-                    } while (jb > jhi);
-                    const float4 rv = row_p[r];
-                    isin = rv.x; icos = rv.y; wrow = rv.z;
-                    rowp = mo + (size_t)(py + band0 + r) * pitch + px;
-                }
-                return true;
-            };
-            // RING steps in flight: the gradient-map load of step k+RING-1 is issued before the votes of step k.  A stage carries the
-            // sample's bin coordinates, weight and gradient; a lane past the end of its row gets cbin = 1e9 (rejected by the reference's
-            // own range test), w < 0 marks a group that has run out of rows.
-            struct Step { float rbin, cbin, w; float2 mo; };
-            auto issue = [&](Step& st) {
-                st.mo = make_float2(0.f, 0.f);
-                st.w = -1.f;
-                if (advance()) {
-                    const int j = jb + gl;
-                    const int jc = min(j, jhi);  // clamped: always a pixel of the interval / a table entry
-                    st.mo = __ldg(rowp + jc);
-                    st.w = wrow * wcol_p[jc - cb0];
-                    const float jf = (float)j;
-                    const float c_rot = jf * cos_t - isin;
-                    const float r_rot = jf * sin_t + icos;
-                    st.rbin = r_rot + DW / 2 - 0.5f;
-                    const float cbin = c_rot + DW / 2 - 0.5f;
-                    st.cbin = j <= jhi ? cbin : 1e9f;
-                }
-            };
-            // one step: the eight trilinear votes of the sample of this lane, branch-free: a rejected sample votes zeros into cell 0
-            auto vote = [&](const Step& st) {
-                const float rbin = st.rbin;
-                float cbin = st.cbin;
-                // floor(rbin) == r0 (this warp's slab) and -1 < cbin < 4 (:620); rbin == -1 exactly (rejected by the reference) votes 0
-                const bool acc = rbin >= r0f && rbin < r1f && cbin > -1 && cbin < DW;
-                const float mag = acc ? st.mo.x * st.w : 0.f;
-                cbin = acc ? cbin : 0.f;
-                const float rf = rbin - r0f;
-                float obin = (st.mo.y - ori) * bins_per_rad;
-                const int c0 = cv_floor(cbin);
-                const int o0 = cv_floor(obin);
-                const float cf = cbin - c0;
-                obin -= o0;
-                // trilinear split in the reference's operation order (:656-662)
-                const float v_r1 = mag * rf, v_r0 = mag - v_r1;
-                float* b = priv + ((c0 + 1) * (DB + 1) + (o0 & (DB - 1))) * DT;  // o0 in [-8, 7]: the reference's two wrap tests == & 7
-                if (has_lo) {
-                    const float v_rc01 = v_r0 * cf, v_rc00 = v_r0 - v_rc01;
-                    float v1;
-                    v1 = v_rc00 * obin; b[0] += v_rc00 - v1; b[DT] += v1;
-                    v1 = v_rc01 * obin; b[(DB + 1) * DT] += v_rc01 - v1; b[(DB + 2) * DT] += v1;
-                }
-                if (has_hi) {
-                    const float v_rc11 = v_r1 * cf, v_rc10 = v_r1 - v_rc11;
-                    float v1;
-                    v1 = v_rc10 * obin; b[PC * (DB + 1) * DT] += v_rc10 - v1; b[(PC * (DB + 1) + 1) * DT] += v1;
-                    v1 = v_rc11 * obin; b[(PC + 1) * (DB + 1) * DT] += v_rc11 - v1; b[((PC + 1) * (DB + 1) + 1) * DT] += v1;
-                }
-            };
-            // ring of four stages, unrolled by four so that a stage is refilled in place (no register shuffling)
-            Step s0, s1, s2, s3;
-            issue(s0); issue(s1); issue(s2); issue(s3);
-            for (;;) {
-                if (s0.w < 0.f) break;
-                vote(s0); issue(s0);
-                if (s1.w < 0.f) break;
-                vote(s1); issue(s1);
-                if (s2.w < 0.f) break;
-                vote(s2); issue(s2);
-                if (s3.w < 0.f) break;
-                vote(s3); issue(s3);
-            }
+        const float rf = rbin - r0f;
+        // trilinear split in the reference's operation order (:656-662)
+        const float v_r1 = mag * rf, v_r0 = mag - v_r1;
+        auto rmw = [&](float* q, float add, bool st_) {
+            const float t = *q + add;
+            if (st_) *q = t;
         };
-        if (s == 0) walk(std::false_type{}, std::true_type{});
-        else if (s == DW) walk(std::true_type{}, std::false_type{});
-        else walk(std::true_type{}, std::true_type{});
+        // buffer 0 = cell-row r0, buffer 1 = cell-row r0+1: every address is one of two registers plus an immediate
+        float* const pA = priv + cA, * const pB = priv + cB;
+        if (HAS_LO) {
+            const float v_rc01 = v_r0 * cf, v_rc00 = v_r0 - v_rc01;
+            float v1;
+            v1 = v_rc00 * obin; rmw(pA + oA, v_rc00 - v1, stA); rmw(pA + oB, v1, stA);
+            v1 = v_rc01 * obin; rmw(pB + oA, v_rc01 - v1, stB); rmw(pB + oB, v1, stB);
+        }
+        if (HAS_HI) {
+            const float v_rc11 = v_r1 * cf, v_rc10 = v_r1 - v_rc11;
+            float v1;
+            v1 = v_rc10 * obin; rmw(pA + ROWBUF + oA, v_rc10 - v1, stA); rmw(pA + ROWBUF + oB, v1, stA);
+            v1 = v_rc11 * obin; rmw(pB + ROWBUF + oA, v_rc11 - v1, stB); rmw(pB + ROWBUF + oB, v1, stB);
+        }
+    };
+    // ring of RING stages (scalar arrays, fully unrolled: everything stays in registers), refilled in place; the list is padded to whole
+    // steps only, so the refill is guarded by a warp-uniform bound
+    float q_rbin[RING], q_cbin[RING], q_w[RING];
+    float2 q_mo[RING];
+#pragma unroll
+    for (int q = 0; q < RING; ++q) {
+        q_rbin[q] = 0.f; q_cbin[q] = 1e9f; q_w[q] = 0.f; q_mo[q] = make_float2(0.f, 0.f);
+        if (q < nsteps) issue(q_rbin[q], q_cbin[q], q_w[q], q_mo[q], q);
     }
-    __syncthreads();
-
-    // ---- tail, stage A: column sums over the 32 private copies of each (slab, cell-row, cell 0..3, bin) (rotated read: conflict-free) ----
-    for (int sidx = tid; sidx < NSUM; sidx += DT) {
-        const int q = sidx / (2 * DW * (DB + 1)), rem = sidx - q * (2 * DW * (DB + 1));
-        const int lr = rem / (DW * (DB + 1)), cb = rem - lr * (DW * (DB + 1));  // cb = cell * 9 + bin
-        const float* col = s_priv + ((lr * PC + 1) * (DB + 1) + cb) * DT + q * 32;  // private cell index = cell + 1
-        float acc = 0.f;
-#pragma unroll 16
-        for (int g = 0; g < 32; ++g) acc += col[(g + tid) & 31];
-        s_sum[sidx] = acc;
+#pragma unroll 1
+    for (int k = 0; k < nsteps; k += RING) {
+#pragma unroll
+        for (int q = 0; q < RING; ++q) {
+            if (q == 0 || k + q < nsteps) {
+                vote(q_rbin[q], q_cbin[q], q_w[q], q_mo[q]);
+                if (k + q + RING < nsteps) issue(q_rbin[q], q_cbin[q], q_w[q], q_mo[q], k + q + RING);
+            }
+        }
     }
-    __syncthreads();
-    // ---- stage B: output element e = (a*4 + b)*8 + k, one per thread; cell-row a = slab a+1's row r0 plus slab a's row r0+1 ----
-    float v = 0.f;
-    if (tid < 128) {
-        const int e_cell = tid >> 3, e_k = tid & 7;
-        const int e_a = e_cell >> 2, e_b = e_cell & 3;
-        const float* lo = s_sum + ((e_a + 1) * 2 + 0) * (DW * (DB + 1)) + e_b * (DB + 1);
-        const float* hi = s_sum + (e_a * 2 + 1) * (DW * (DB + 1)) + e_b * (DB + 1);
-        v = lo[e_k] + hi[e_k];
-        if (e_k == 0) v += lo[DB] + hi[DB];  // hist[idx] += hist[idx+n] (:680); hist[idx+n+1] is never written since o0 <= n-1
-    }
-    float nrm2 = block_sum(v * v, s_red, tid);
-    const float thr = sqrtf(nrm2) * 0.2f;
-    v = fminf(v, thr);
-    nrm2 = block_sum(v * v, s_red, tid);
-    nrm2 = 512.f / fmaxf(sqrtf(nrm2), 1.1920928955078125e-7f);
-    int u = __float2int_rn(v * nrm2);  // saturate_cast<uchar>: round half to even, clamp to 0..255
-    u = min(max(u, 0), 255);
-    v = (float)u * nrm2;
-    float nrm1 = block_sum(v, s_red, tid);
-    nrm1 = 1.f / fmaxf(nrm1, 1.1920928955078125e-7f);
-    if (tid < 128) dst[tid] = sqrtf(v * nrm1);
-    __syncthreads();
 }
 
-__global__ void __launch_bounds__(DT, CTAS_PER_SM)
-    describe_kernel(const __grid_constant__ PyrView pv, const DetectBuf db, SiftKeypoint* __restrict__ kp_out, float* __restrict__ desc_out, int cap,
-                    float gl_div) {
-    extern __shared__ __align__(16) float smem[];
+// calcSIFTDescriptor, src/sift.cpp:579-722, for one keypoint by one warp.  dst: 128 floats in global memory.
+// mo: the level's gradient map {Mag, Ori} (detect.cu gradient_kernel) -- the values the reference computes per sample (:623-633).
+// smem: this warp's WARP_FLOATS floats.
+__device__ void calc_descriptor(const float2* __restrict__ mo, int pitch, const DescParams& P, float* __restrict__ smem, float* __restrict__ dst) {
+    const int lane = threadIdx.x & 31;
+    const float cos_t = P.cos_t, sin_t = P.sin_t, es = P.es;
+    float* s_priv = smem;                                            // [2][PC][PB][32]
+    float4* s_rowA = reinterpret_cast<float4*>(smem + 2 * ROWBUF);   // [NB+1] {i*sin_t, i*cos_t, wrow, (int) element offset of the row}; [NB]: dummy
+    float* s_wcol = reinterpret_cast<float*>(s_rowA + NB + 1);       // [WCOL] wcol[j - cb0]
+    int* s_chunk = reinterpret_cast<int*>(s_wcol + WCOL);            // [NCHUNK + NPAD] row | (j0 - cb0) << 8 | pixels << 16
+    float* priv = s_priv + lane;
+    const int grp = lane >> 2, gl = lane & 3;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const bool single = P.imax - P.imin < NB && P.jmax - P.jmin < WCOL;  // the whole window is one block (every pipeline keypoint)
+    {   // keep the level pointer as one opaque 64-bit value: a sample address is then a single multiply-add on a 32-bit index
+        unsigned long long m = reinterpret_cast<unsigned long long>(mo);
+        asm volatile("" : "+l"(m));
+        mo = reinterpret_cast<const float2*>(m);
+    }
+
+    for (int k = lane * 4; k < 2 * ROWBUF; k += 128) *reinterpret_cast<float4*>(s_priv + k) = make_float4(0.f, 0.f, 0.f, 0.f);
+    float v[DW];  // lane l: output element (cell-row a, l) = (a, cell l >> 3, bin l & 7)
+#pragma unroll
+    for (int a = 0; a < DW; ++a) v[a] = 0.f;
+
+#pragma unroll 1
+    for (int s = 0; s < NSLAB; ++s) {
+        const float r0f = (float)(s - 1), r1f = (float)s;
+        // The window is processed in blocks of NB rows x WCOL columns so that the tables fit shared memory whatever the keypoint size.
+#pragma unroll 1
+        for (int band0 = P.imin; band0 <= P.imax; band0 += NB)
+#pragma unroll 1
+        for (int cb0 = P.jmin; cb0 <= P.jmax; cb0 += WCOL) {
+            const int nrows = min(NB, P.imax - band0 + 1);
+            const int cb1 = min(P.jmax, cb0 + WCOL - 1);
+            if (!single || s == 0) {
+                __syncwarp();
+                for (int k = lane; k <= cb1 - cb0; k += 32) s_wcol[k] = expf((float)((cb0 + k) * (cb0 + k)) * es);
+                // dummy row for the padding chunks: a readable pixel, weight 0, row coordinate far outside every slab
+                if (lane == 0) s_rowA[NB] = make_float4(0.f, 1e9f, 0.f, __int_as_float((P.py + band0) * pitch + P.px));
+                for (int r = lane; r < nrows; r += 32) {
+                    const int i = band0 + r;
+                    s_rowA[r] = make_float4(i * sin_t, i * cos_t, expf((float)(i * i) * es), __int_as_float((P.py + i) * pitch + P.px));
+                }
+            }
+            __syncwarp();
+            // rows the slab can touch: i = hw^2 (cos_t (rbin - 1.5) - sin_t (cbin - 1.5)) over the slab's corners rbin in {r0, r0+1},
+            // cbin in {-1, 4}, widened by a row each side (the exact tests below decide); only those 32-row rounds are visited
+            int rb_first, rb_end;
+            {
+                const float hw2 = 1.f / (cos_t * cos_t + sin_t * sin_t);
+                const float ar0 = cos_t * (r0f - 1.5f) * hw2, ar1 = cos_t * (r1f - 1.5f) * hw2;
+                const float ac0 = sin_t * 2.5f * hw2, ac1 = -ac0;  // -sin_t * (cbin - 1.5) for cbin = -1 and 4
+                const float i_lo = fminf(ar0, ar1) + fminf(ac0, ac1), i_hi = fmaxf(ar0, ar1) + fmaxf(ac0, ac1);
+                const int r_lo = max(0, (int)floorf(i_lo) - 1 - band0), r_hi = min(nrows - 1, (int)ceilf(i_hi) + 1 - band0);
+                rb_first = r_lo & ~31;
+                rb_end = r_hi + 1;
+            }
+            int pass0 = 0, total;
+            do {
+                // ---- chunk list of this slab: every row interval cut into pieces of <= 4 pixels, in row-major order ----
+                total = 0;
+                for (int rb = rb_first; rb < rb_end; rb += 32) {
+                    const int r = rb + lane;
+                    int cnt = 0, jlo = 0, jhi = -1;
+                    if (r < nrows) {
+                        const float4 rv = s_rowA[r];
+                        // the column-slab interval -1 < cbin < 4, then the row-slab interval r0 <= rbin < r0+1
+                        float lo = (float)cb0, hi = (float)cb1;
+                        const bool ok = slab(P.inv_c, P.mar_c, -rv.x + 1.5f, -1.f, 4.f, lo, hi) && slab(P.inv_s, P.mar_s, rv.y + 1.5f, r0f, r1f, lo, hi);
+                        jlo = max(cb0, (int)ceilf(lo)); jhi = min(cb1, (int)floorf(hi));
+                        if (ok && jlo <= jhi) cnt = (jhi - jlo + 4) >> 2;
+                    }
+                    // exclusive prefix sum of cnt (< 32) over the lanes: five independent ballots instead of a five-deep shuffle chain
+                    int excl = 0;
+#pragma unroll
+                    for (int bit = 0; bit < 5; ++bit) excl += __popc(__ballot_sync(0xffffffffu, (cnt >> bit) & 1) & lt_mask) << bit;
+                    const int base = total + excl - pass0;
+                    for (int c = 0; c < cnt; ++c) {
+                        const int idx = base + c;
+                        if (idx >= 0 && idx < NCHUNK)
+                            s_chunk[idx] = r | ((jlo + 4 * c - cb0) << 8) | (min(4, jhi - jlo - 4 * c + 1) << 16);
+                    }
+                    total += __shfl_sync(0xffffffffu, excl + cnt, 31);
+                }
+                const int nchunks = min(NCHUNK, total - pass0);
+                const int nsteps = (nchunks + 7) >> 3;
+                // padding chunks (dummy row, one pixel at cb0) up to a whole step: the walk needs no per-lane bounds test
+                if (nchunks + lane < nsteps * 8) s_chunk[nchunks + lane] = NB | (1 << 16);
+                __syncwarp();
+#if DESC_ROLES
+                if (s == 0) walk_slab<false, true>(mo, s_rowA, s_wcol, s_chunk, nsteps, cb0, cos_t, sin_t, P.ori, r0f, r1f, priv, grp, gl);
+                else if (s == DW) walk_slab<true, false>(mo, s_rowA, s_wcol, s_chunk, nsteps, cb0, cos_t, sin_t, P.ori, r0f, r1f, priv, grp, gl);
+                else walk_slab<true, true>(mo, s_rowA, s_wcol, s_chunk, nsteps, cb0, cos_t, sin_t, P.ori, r0f, r1f, priv, grp, gl);
+#else
+                // one instantiation for all slabs (smaller code): the border slabs vote their out-of-grid half into the other buffer's
+                // scratch -- buffer 0 of slab 0 and buffer 1 of slab 4 are never summed
+                walk_slab<true, true>(mo, s_rowA, s_wcol, s_chunk, nsteps, cb0, cos_t, sin_t, P.ori, r0f, r1f, priv, grp, gl);
+#endif
+                __syncwarp();
+                pass0 += NCHUNK;
+            } while (pass0 < total);
+        }
+        // ---- slab done.  Buffer 0 holds cell-row a = s-1, now complete: sum its 4 x 9 bins over the 32 lane-private copies and fold the
+        // circular bin.  Then buffer 1 (cell-row s, half done) becomes buffer 0 of the next slab and buffer 1 is cleared. ----
+        if (s >= 1) {
+            const int a = s - 1;
+            const int cell = lane >> 3, k = lane & 7;
+            // lane l reads copies 4q'..4q'+3 of ITS bin with q' = (q + l) & 7: the 8 lanes of a quarter-warp hit 8 different 16-byte bank groups
+            auto colsum = [&](int bin) {
+                const float* col = s_priv + ((cell + C1) * PB + bin) * 32;
+                float acc = 0.f;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const float4 t = *reinterpret_cast<const float4*>(col + (((q + lane) & 7) << 2));
+                    acc += (t.x + t.y) + (t.z + t.w);
+                }
+                return acc;
+            };
+            float e = colsum(k);
+            if (PB == 9 && k == 0) e += colsum(DB);  // hist[idx] += hist[idx+n] (:680); hist[idx+n+1] is never written since o0 <= n-1
+#pragma unroll
+            for (int q = 0; q < DW; ++q)
+                if (q == a) v[q] = e;
+            __syncwarp();
+        }
+        if (s < NSLAB - 1) {
+            for (int i = lane * 4; i < ROWBUF; i += 128) {
+                *reinterpret_cast<float4*>(s_priv + i) = *reinterpret_cast<const float4*>(s_priv + ROWBUF + i);
+                *reinterpret_cast<float4*>(s_priv + ROWBUF + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            __syncwarp();
+        }
+    }
+
+    // ---- tail (:689-721): L2 norm, clamp at 0.2, renormalise to 512, uchar, L1, sqrt ----
+    float part = 0.f;
+#pragma unroll
+    for (int a = 0; a < DW; ++a) part += v[a] * v[a];
+    float nrm2 = warp_sum(part);
+    const float thr = sqrtf(nrm2) * 0.2f;
+    part = 0.f;
+#pragma unroll
+    for (int a = 0; a < DW; ++a) { v[a] = fminf(v[a], thr); part += v[a] * v[a]; }
+    nrm2 = warp_sum(part);
+    nrm2 = 512.f / fmaxf(sqrtf(nrm2), 1.1920928955078125e-7f);
+    part = 0.f;
+#pragma unroll
+    for (int a = 0; a < DW; ++a) {
+        int u = __float2int_rn(v[a] * nrm2);  // saturate_cast<uchar>: round half to even, clamp to 0..255
+        u = min(max(u, 0), 255);
+        v[a] = (float)u * nrm2;
+        part += v[a];
+    }
+    float nrm1 = warp_sum(part);
+    nrm1 = 1.f / fmaxf(nrm1, 1.1920928955078125e-7f);
+#pragma unroll
+    for (int a = 0; a < DW; ++a) dst[a * 32 + lane] = sqrtf(v[a] * nrm1);
+}
+
+// Per output keypoint: DescParams record + the cv::KeyPoint record (unpackOctave :724-731, calDescriptor :739-749).
+__global__ void __launch_bounds__(128) describe_prep_kernel(const __grid_constant__ PyrView pv, const DetectBuf db, SiftKeypoint* __restrict__ kp_out, int cap) {
     const int f = blockIdx.y;
     int n = db.n_refined[f];
     if (n > db.cap_r) n = db.cap_r;
-    for (int p = blockIdx.x; p < n; p += gridDim.x) {
-        const int i = db.order[(size_t)f * db.cap_r + p];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const Refined rec = db.refined[(size_t)f * db.cap_r + i];
         const int np = db.n_peaks[(size_t)f * db.cap_r + i];
         const int base = db.kp_offset[(size_t)f * db.cap_r + i];
-        // unpackOctave (:724-731); firstOctave = 0 in SIFT_NCL (:86)
+        // firstOctave = 0 in SIFT_NCL (:86)
         const int octave = rec.octave & 255, layer = (rec.octave >> 8) & 255;
         const float scale = 1.f / (1 << octave);
         const OctaveView& ov = pv.oct[octave];
-        const float2* img = ov.MO[layer] + (size_t)f * ov.frame_stride;
         const float size = rec.size * scale;
         for (int k = 0; k < np; ++k) {
             const int slot = base + k;
@@ -310,62 +411,89 @@ __global__ void __launch_bounds__(DT, CTAS_PER_SM)
             const float kp_angle = db.angles[((size_t)f * db.cap_r + i) * kMaxPeaks + k];
             float angle = 360.f - kp_angle;
             if (fabsf(angle - 360.f) < 1.1920928955078125e-7f) angle = 0.f;
-            calc_descriptor(img, ov.rows, ov.cols, ov.pitch, rec.x * scale, rec.y * scale, angle, size * 0.5f, gl_div, smem,
-                            desc_out + ((size_t)f * cap + slot) * 128);
-            if (threadIdx.x == 0) {
-                SiftKeypoint kp;
-                kp.x = rec.x; kp.y = rec.y; kp.size = rec.size; kp.angle = kp_angle; kp.response = rec.response;
-                kp.octave = rec.octave; kp.class_id = -1;
-                kp_out[(size_t)f * cap + slot] = kp;
-            }
+            db.dparams[(size_t)f * db.cap_r + slot] = make_params(ov.rows, ov.cols, octave | (layer << 8), rec.x * scale, rec.y * scale, angle, size * 0.5f);
+            SiftKeypoint kp;
+            kp.x = rec.x; kp.y = rec.y; kp.size = rec.size; kp.angle = kp_angle; kp.response = rec.response;
+            kp.octave = rec.octave; kp.class_id = -1;
+            kp_out[(size_t)f * cap + slot] = kp;
         }
     }
 }
 
 // calDescriptor on caller-supplied keypoints (stage-level API): any octave/layer the reference's CV_Assert admits.
-__global__ void __launch_bounds__(DT, CTAS_PER_SM)
-    describe_given_kernel(const __grid_constant__ PyrView pv, const SiftKeypoint* __restrict__ kps, int n, float* __restrict__ desc_out, int first_octave,
-                          int* __restrict__ err, float gl_div) {
-    extern __shared__ __align__(16) float smem[];
-    for (int p = blockIdx.x; p < n; p += gridDim.x) {
+__global__ void __launch_bounds__(128) describe_prep_given_kernel(const __grid_constant__ PyrView pv, const SiftKeypoint* __restrict__ kps, int n,
+                                                                  DescParams* __restrict__ params, int first_octave, int* __restrict__ err) {
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
         const SiftKeypoint kp = kps[p];
         int octave = kp.octave & 255;
         const int layer = (kp.octave >> 8) & 255;
         octave = octave < 128 ? octave : (-128 | octave);
         const float scale = octave >= 0 ? 1.f / (1 << octave) : (float)(1 << -octave);
         if (!(octave >= first_octave && layer <= kOctaveLayers + 2) || octave - first_octave >= pv.n_oct || layer >= kNumScales) {
-            if (threadIdx.x == 0) atomicExch(err, 1);  // CV_Assert, src/sift.cpp:744
+            atomicExch(err, 1);  // CV_Assert, src/sift.cpp:744
+            DescParams P{};
+            P.level = -1;
+            params[p] = P;
             continue;
         }
         const OctaveView& ov = pv.oct[octave - first_octave];
         float angle = 360.f - kp.angle;
         if (fabsf(angle - 360.f) < 1.1920928955078125e-7f) angle = 0.f;
         const float size = kp.size * scale;
-        calc_descriptor(ov.MO[layer], ov.rows, ov.cols, ov.pitch, kp.x * scale, kp.y * scale, angle, size * 0.5f, gl_div, smem, desc_out + (size_t)p * 128);
+        params[p] = make_params(ov.rows, ov.cols, (octave - first_octave) | (layer << 8), kp.x * scale, kp.y * scale, angle, size * 0.5f);
     }
 }
 
-float g_gl_div = 1.5f;
+// counts == nullptr: one list of n_fixed records (stage-level API); else frame f = blockIdx.y has min(counts[f], cap) records at stride pstride.
+__global__ void __launch_bounds__(DESC_WARPS * 32, DESC_MIN_CTAS)
+    describe_kernel(const __grid_constant__ PyrView pv, const DescParams* __restrict__ params, const int* __restrict__ counts, int n_fixed, int cap, int pstride,
+                    float* __restrict__ desc_out) {
+    extern __shared__ __align__(16) float smem_all[];
+    const int warp = threadIdx.x >> 5;
+    float* smem = smem_all + warp * WARP_FLOATS;
+    const int f = blockIdx.y;
+    const int n = counts ? min(counts[f], cap) : n_fixed;
+    const DescParams* mine = params + (size_t)f * pstride;
+    float* out = desc_out + (size_t)f * cap * 128;
+    const int stride = gridDim.x * DESC_WARPS;
+    int p = blockIdx.x * DESC_WARPS + warp;
+    if (p >= n) return;
+    DescParams P = mine[p];
+    for (; p < n; p += stride) {
+        const DescParams cur = P;
+        if (p + stride < n) P = mine[p + stride];  // next record in flight while this keypoint is processed
+        if (cur.level < 0) continue;
+        const OctaveView& ov = pv.oct[cur.level & 255];
+        const float2* img = ov.MO[cur.level >> 8] + (size_t)f * ov.frame_stride;
+        calc_descriptor(img, ov.pitch, cur, smem, out + (size_t)p * 128);
+    }
+}
 
 }  // namespace
 
+namespace {
+int g_grid_div = 1;  // CTAs per frame = resident CTAs of the device / g_grid_div (tuning probe, env SIFT_B200_DESC_GRIDDIV)
+}
+
 void init_describe_kernels() {
     cudaFuncSetAttribute(describe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DESC_SMEM_BYTES);
-    cudaFuncSetAttribute(describe_given_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DESC_SMEM_BYTES);
-    if (const char* e = getenv("SIFT_B200_DESC_GLDIV")) g_gl_div = (float)atof(e);  // tuning probe: run length per group lane count
+    if (const char* e = getenv("SIFT_B200_DESC_GRIDDIV")) g_grid_div = atoi(e) > 0 ? atoi(e) : 1;
 }
 
 int launch_describe(const PyrView& pv, const DetectBuf& db, int n_frames, SiftKeypoint* d_kp, float* d_desc, int cap, cudaStream_t st) {
-    dim3 grid(num_sms() * CTAS_PER_SM, n_frames);
-    describe_kernel<<<grid, DT, DESC_SMEM_BYTES, st>>>(pv, db, d_kp, d_desc, cap, g_gl_div);
-    return 1;
+    describe_prep_kernel<<<dim3(16, n_frames), 128, 0, st>>>(pv, db, d_kp, cap);
+    const int per_frame = (num_sms() * CTAS_PER_SM + g_grid_div - 1) / g_grid_div;
+    describe_kernel<<<dim3(per_frame, n_frames), DESC_WARPS * 32, DESC_SMEM_BYTES, st>>>(pv, db.dparams, db.n_kp, 0, cap, db.cap_r, d_desc);
+    return 2;
 }
 
-int launch_describe_given(const PyrView& pv, const SiftKeypoint* d_kps, int n, float* d_desc, int first_octave, int* d_err, cudaStream_t st) {
+int launch_describe_given(const PyrView& pv, const SiftKeypoint* d_kps, int n, float* d_desc, int first_octave, int* d_err, DescParams* d_params,
+                          cudaStream_t st) {
     if (n <= 0) return 0;
-    const int blocks = n < num_sms() * CTAS_PER_SM ? n : num_sms() * CTAS_PER_SM;
-    describe_given_kernel<<<blocks, DT, DESC_SMEM_BYTES, st>>>(pv, d_kps, n, d_desc, first_octave, d_err, g_gl_div);
-    return 1;
+    describe_prep_given_kernel<<<(n + 127) / 128, 128, 0, st>>>(pv, d_kps, n, d_params, first_octave, d_err);
+    const int blocks = (n + DESC_WARPS - 1) / DESC_WARPS < num_sms() * CTAS_PER_SM ? (n + DESC_WARPS - 1) / DESC_WARPS : num_sms() * CTAS_PER_SM;
+    describe_kernel<<<blocks, DESC_WARPS * 32, DESC_SMEM_BYTES, st>>>(pv, d_params, nullptr, n, n, 0, d_desc);
+    return 2;
 }
 
 }  // namespace siftb200

@@ -465,6 +465,7 @@ __global__ void __launch_bounds__(SORT_THREADS) order_scan_kernel(const DetectBu
     }
     if (tid == 0) {
         int total = s_carry;
+        db.n_kp[f] = total;  // what the descriptor stage iterates over
         // a full candidate / refined list means keypoints were dropped: report a count above any admissible cap
         if (db.n_refined[f] > db.cap_r || db.n_cand[f] > db.cap_c) total = max(total, db.cap_r + 1);
         counts_out[f] = total;

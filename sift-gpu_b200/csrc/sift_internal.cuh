@@ -51,6 +51,20 @@ struct Refined {
     uint32_t pad;
 };
 
+// Everything calcSIFTDescriptor derives from the keypoint alone (describe.cu: describe_prep_kernel writes one per output keypoint).
+struct DescParams {
+    float cos_t, sin_t;          // rotation divided by the cell width 3*scl (src/sift.cpp:594-596)
+    float es;                    // exponent scale of the separable Gaussian weight
+    float ori;                   // 360 - kpt.angle, degrees
+    float inv_s, inv_c;          // 1/sin_t, 1/cos_t for the slab intervals (0: flat direction)
+    float mar_s, mar_c;          // interval margins
+    int px, py;                  // cvRound of the keypoint position in octave coordinates
+    int jmin, jmax, imin, imax;  // window clipped to 0 < r < rows-1, 0 < c < cols-1
+    int level;                   // octave index | layer << 8; -1: rejected by the reference's CV_Assert
+    int pad;
+};
+static_assert(sizeof(DescParams) == 64, "DescParams is read as four 16-byte words");
+
 struct DetectBuf {
     uint32_t* cand;      // [F][cap_c] scan-order keys of the 27-neighbour extrema (before refinement)
     int* n_cand;         // [F]
@@ -62,6 +76,8 @@ struct DetectBuf {
     int* order;          // [F][cap_r]  sorted position -> refined index
     int* kp_offset;      // [F][cap_r]  refined index -> first output slot
     unsigned long long* sort_tmp; // [F][cap_r_pow2] global scratch when the frame does not fit shared memory
+    DescParams* dparams; // [F][cap_r]  per output keypoint slot
+    int* n_kp;           // [F] output keypoints actually produced (counts_out may carry the overflow sentinel instead)
     int cap_r;
     int cap_r_pow2;
 };
@@ -95,7 +111,8 @@ int launch_extrema(const PyrView& pv, const DetectBuf& db, int n_frames, cudaStr
 int launch_orientation(const PyrView& pv, const DetectBuf& db, int n_frames, cudaStream_t st);
 int launch_order_scan(const DetectBuf& db, int n_frames, int* d_counts, cudaStream_t st);
 int launch_describe(const PyrView& pv, const DetectBuf& db, int n_frames, SiftKeypoint* d_kp, float* d_desc, int cap, cudaStream_t st);
-int launch_describe_given(const PyrView& pv, const SiftKeypoint* d_kps, int n, float* d_desc, int first_octave, int* d_err, cudaStream_t st);
+int launch_describe_given(const PyrView& pv, const SiftKeypoint* d_kps, int n, float* d_desc, int first_octave, int* d_err, DescParams* d_params,
+                          cudaStream_t st);
 int launch_match(const float* d_q, int nq, const float* d_t, int nt, int norm, float* d_dist, int32_t* d_idx, cudaStream_t st);
 // tcgen05 L2 matcher: bf16 hi/lo operand tiles -> tensor-core shortlists -> exact fp64 re-rank (match_tc.cu)
 size_t match_tc_scratch_bytes(int nq, int nt);

@@ -66,11 +66,14 @@ def test_descriptor_stage_on_oracle_inputs(sift, oracle, synth, w, h, seed):
 # Descriptor gates for the default (separable-blur) pipeline, whole path.  North star: L2 <= 1e-3.  The reference quantises to uchar
 # inside the float pipeline (src/sift.cpp:709), so the ~1e-4 rounding difference between the separable blur and the reference's
 # 1369-term sequential sum flips one +-1 LSB in a few per cent of rows, and one flip moves a component by >= 1.2e-3.
-# Gates: (a) the fraction of rows within 1e-3 may not fall below the observed floor (MIN_FRAC: regressions trip), (b) EVERY row
-# beyond 1e-3 must be an explained flip -- all differing quantised integers differ by exactly 1 and the reference's pre-quantisation
-# value sat within parity.QUANT_EDGE of a rounding boundary -- i.e. unexplained == 0, with the reference's own pre-quantisation
-# vectors (fixtures *_prequant.npz, legitimate because the C port is bit-identical to oracle/_ref on those images).
-MIN_FRAC = 0.93
+# Gates: (a) the fraction of rows within 1e-3 may not fall below the observed floor (MIN_FRAC: regressions trip; observed 0.955-0.993
+# over the eight test images, tools/parity_report.py), (b) EVERY row beyond 1e-3 must be explained -- either a quantisation flip (all
+# differing quantised integers differ by exactly 1 and the reference's pre-quantisation value sat within parity.QUANT_EDGE of a
+# rounding boundary) or a keypoint whose interpolated orientation differs by a fraction of a degree (inside the 1 deg tolerance)
+# and whose descriptor is right once the descriptor stage is fed the reference's keypoint record (parity.classify_unexplained)
+# -- i.e. unexplained == 0, with the reference's own pre-quantisation vectors (fixtures *_prequant.npz, legitimate because the C
+# port is bit-identical to oracle/_ref on those images).
+MIN_FRAC = 0.95
 
 
 def _end_to_end(sift, img, okp, odesc, opq, min_frac=MIN_FRAC):
@@ -80,9 +83,12 @@ def _end_to_end(sift, img, okp, odesc, opq, min_frac=MIN_FRAC):
     rec, prec = parity.recall_precision(pairs, len(kp), len(okp))
     assert rec >= 0.99 and prec >= 0.99, (rec, prec, len(kp), len(okp))
     pi = np.array([p[0] for p in pairs]); pj = np.array([p[1] for p in pairs])
-    frac, explained, unexplained, mx = parity.descriptor_report(desc[pi], odesc[pj], opq[pj])
+    rows = []
+    frac, explained, unexplained, mx = parity.descriptor_report(desc[pi], odesc[pj], opq[pj], rows_out=rows)
     assert frac >= min_frac, (frac, explained, unexplained, mx)
-    assert unexplained == 0, (frac, explained, unexplained, mx)
+    by_keypoint, unexplained = parity.classify_unexplained(sift, img, kp[pi], okp[pj], odesc[pj], opq[pj], rows)
+    assert unexplained == 0, (frac, explained, by_keypoint, unexplained, mx)
+    assert by_keypoint <= max(2, len(pairs) // 100), (frac, explained, by_keypoint, mx)  # observed <= 0.3 % of rows
     # output order = reference scan order (src/sift.cpp:556-557,487,491,525): matched pairs are index-aligned
     if len(kp) == len(okp) and len(pairs) == len(kp):
         assert all(i == j for i, j, _, _ in pairs)

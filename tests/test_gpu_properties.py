@@ -36,12 +36,9 @@ def test_1080p_vs_oracle(sift, oracle, frame1080):
     """BASELINE config 2 at full size: the oracle needs ~1 s for this frame with all cores."""
     okp, odesc, _, _, opq = oracle.f32().sift_ncl(frame1080, want_pyramids=True, want_prequant=True)
     kp, desc = sift.detect_describe(frame1080)
-    pairs = parity.match_keypoints(kp, okp)
-    rec, prec = parity.recall_precision(pairs, len(kp), len(okp))
-    assert rec >= 0.99 and prec >= 0.99
-    pi = np.array([p[0] for p in pairs]); pj = np.array([p[1] for p in pairs])
-    frac, explained, unexplained, mx = parity.descriptor_report(desc[pi], odesc[pj], opq[pj])
-    assert frac >= 0.95 and unexplained <= len(pairs) // 200, (frac, explained, unexplained, mx)
+    r = parity.full_report(sift, frame1080, kp, desc, okp, odesc, opq)
+    assert r["kp_recall"] >= 0.99 and r["kp_precision"] >= 0.99, r
+    assert r["frac_within_1e-3"] >= 0.95 and r["unexplained"] == 0 and r["explained_by_keypoint"] <= r["matched"] // 100, r
 
 
 def test_batch_dev_equals_single_frames(pkg, synth):
@@ -195,9 +192,8 @@ def test_upsample_front_end_and_config3(pkg, oracle, synth):
     pairs = parity.match_keypoints(kp, okp)
     rec, prec = parity.recall_precision(pairs, len(kp), len(okp))
     assert len(okp) > 5000 and rec >= 0.99 and prec >= 0.99, (len(kp), len(okp), rec, prec)
-    pi = np.array([p[0] for p in pairs]); pj = np.array([p[1] for p in pairs])
-    frac, explained, unexplained, mx = parity.descriptor_report(desc[pi], odesc[pj], opq[pj])
-    assert frac >= 0.93 and unexplained <= len(pairs) // 200, (frac, explained, unexplained, mx)
+    r = parity.full_report(s, want_up, kp, desc, okp, odesc, opq)
+    assert r["frac_within_1e-3"] >= 0.95 and r["unexplained"] == 0 and r["explained_by_keypoint"] <= r["matched"] // 100, r
     s.close()
 
 

@@ -1,4 +1,4 @@
-"""The C oracle against oracle/_ref (the unmodified reference compiled against oracle/cvshim), run live on seeded
+"""The C oracle against oracle/_ref (the unmodified reference compiled against third_party/cvshim), run live on seeded
 inputs including the edge cases the reference admits.  Skipped when oracle/_ref was not built (no /root/reference)."""
 import numpy as np
 import pytest
