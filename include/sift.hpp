@@ -5,14 +5,37 @@
 // (src/main.cpp:23-24) and nothing else.  The bodies live in sift-gpu_b200/host/sift_dropin.cpp and forward to
 // the C ABI of include/sift_b200.h (hand-written sm_100a kernels); there is no CPU implementation behind them.
 //
-// Needs OpenCV 4 core headers for cv::Mat / cv::KeyPoint / InputArray / OutputArray.  In the build container, where
-// OpenCV C++ is absent, oracle/cvshim stands in for compile- and run-checks.
+// Includes what the reference header includes (reference include/sift.hpp:11-25), because its includers rely on it: the unchanged
+// src/main.cpp gets imread, resize, cvtColor, BFMatcher, findHomography, imshow and <iostream> through this header alone.  The
+// contrib module xfeatures2d is optional here (only SITF_BuildIn_OpenCV uses it): without it the namespace is declared empty so
+// that the reference's `using namespace cv::xfeatures2d;` still compiles.  In the build container, where OpenCV C++ is absent,
+// third_party/cvshim stands in for compile- and run-checks.
 #ifndef SIFT_HPP_
 #define SIFT_HPP_
 
+#include <stdio.h>
+#include <stdlib.h>
+
+#include <iostream>
 #include <vector>
 
 #include <opencv2/core.hpp>
+#include <opencv2/core/utility.hpp>
+#include <opencv2/imgcodecs.hpp>
+#include <opencv2/imgproc.hpp>
+#include <opencv2/features2d.hpp>
+#include <opencv2/highgui.hpp>
+#include <opencv2/calib3d/calib3d.hpp>
+#if defined(__has_include)
+#if __has_include(<opencv2/core/types_c.h>)
+#include <opencv2/core/types_c.h>  // cvPoint (src/main.cpp:59-60)
+#endif
+#if __has_include(<opencv2/xfeatures2d.hpp>)
+#include <opencv2/xfeatures2d.hpp>
+#define SIFT_B200_HAVE_XFEATURES2D 1
+#endif
+#endif
+namespace cv { namespace xfeatures2d {} }
 
 // The reference header injects both namespaces and these two names into every includer; main.cpp relies on it.
 using namespace cv;

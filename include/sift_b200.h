@@ -94,6 +94,13 @@ int sift_b200_detect_describe_batch_dev_u8(SiftB200* h, const uint8_t* d_imgs, i
  * d_gray [n_frames][rows][cols] u8 (feed it to ..._batch_dev_u8), asynchronous on `stream`. */
 int sift_b200_rgb2gray_u8_dev(SiftB200* h, const uint8_t* d_bgr, int n_frames, int rows, int cols, uint8_t* d_gray, void* stream);
 
+/* The rest of the driver's readImage (src/main.cpp:79-87) on host buffers, synchronous:
+ *   resize_linear_u8: resize(img, img, Size(960,960)) (:83) = cv::resize(INTER_LINEAR) on 8-bit pixels with 1..4 interleaved channels,
+ *                     OpenCV's fixed-point bilinear (11-bit coefficients), bit-identical to cv2.resize;
+ *   rgb2gray_u8:      cvtColor(img, gray, COLOR_RGB2GRAY) (:84) on the BGR bytes imread returns (host form of ..._rgb2gray_u8_dev). */
+int sift_b200_resize_linear_u8(SiftB200* h, const uint8_t* src, int rows, int cols, int channels, uint8_t* dst, int drows, int dcols);
+int sift_b200_rgb2gray_u8(SiftB200* h, const uint8_t* bgr, int rows, int cols, uint8_t* gray);
+
 /* 2x bilinear upsample front end (BASELINE config 3; the reference ignores doubleSize, src/sift.cpp:219-227, so this is an
  * extension with cv::resize(INTER_LINEAR) semantics: half-pixel centres, edge replicate).
  * Device: d_src [n_frames][rows][cols] -> d_dst [n_frames][2*rows][2*cols], asynchronous on `stream`; feed d_dst to
@@ -146,6 +153,17 @@ int sift_b200_match_knn2_ex(SiftB200* h, const float* query, int nq, const float
  * synchronised by the caller).  The ratio test is left to the caller (two floats). */
 int sift_b200_match_knn2_dev(SiftB200* h, const float* d_query, int nq, const float* d_train, int nt, int norm, int32_t* d_idx,
                              float* d_dist, int tensor_cores, void* stream);
+
+/* ---- homography consumer (src/main.cpp:44-62) ------------------------------------------------------- */
+/* findHomography(src, dst, RANSAC, ransac_thresh) over n correspondences given as interleaved (x, y) float pairs (the driver passes
+ * the query / scene keypoint positions of the ratio-test survivors, :48-53).  max_iters hypotheses (<= 0: OpenCV's default 2000) are
+ * evaluated in parallel on the device; the consensus set of the best one (ties: lowest index -- the call is deterministic) is refitted
+ * in double: normalised DLT, then Levenberg-Marquardt on the reprojection error, as OpenCV does after its RANSAC loop.  Outputs:
+ * H9_out row-major 3x3 with h33 = 1, mask_out[n] (optional) = consensus set, *n_inliers_out.  ERR_TOO_SMALL when n < 4 or no
+ * non-degenerate sample exists (cv::findHomography returns an empty Mat).  OpenCV's random sequence is not reproduced: the parity
+ * bar is "same consensus set, same refit" (tests), not bit identity. */
+int sift_b200_find_homography(SiftB200* h, const float* src_xy, const float* dst_xy, int n, double ransac_thresh, int max_iters,
+                              double* H9_out, uint8_t* mask_out, int* n_inliers_out);
 
 /* Chunk schedule of the host-batch entry points for n_frames frames on a handle created with max_batch (pure host logic, no
  * device needed): writes up to plan_cap chunk sizes, returns the number of chunks (or -1 on a bad argument).  Every chunk is in

@@ -32,7 +32,7 @@ ABI_SYMBOLS = [
     "sift_b200_detect_describe_batch_host_u8", "sift_b200_detect_describe_batch_dev_u8", "sift_b200_rgb2gray_u8_dev", "sift_b200_upsample2x_dev", "sift_b200_detect_describe_up2", "sift_b200_gaussian_blur", "sift_b200_gaussian_blur_1d",
     "sift_b200_build_gaussian_pyramid", "sift_b200_build_dog_pyramid", "sift_b200_find_scale_space_extrema",
     "sift_b200_cal_descriptor", "sift_b200_match_knn2", "sift_b200_match_knn2_ex", "sift_b200_match_knn2_dev", "sift_b200_set_exact_pyramid", "sift_b200_launch_count", "sift_b200_set_stage_timing",
-    "sift_b200_get_stage_ms", "sift_b200_chunk_plan",
+    "sift_b200_get_stage_ms", "sift_b200_chunk_plan", "sift_b200_resize_linear_u8", "sift_b200_rgb2gray_u8", "sift_b200_find_homography",
 ]
 
 
@@ -210,6 +210,37 @@ class Sift:
         desc = np.zeros((len(kps), 128), dtype=np.float32)
         self._check(lib().sift_b200_cal_descriptor(self._h, _p(gpyr), rows, cols, n_octaves, _p(kps), len(kps), _p(desc), first_octave))
         return desc
+
+    # ---- the driver's readImage and homography consumer (src/main.cpp:79-87, 44-62) ----
+    def resize_linear_u8(self, img: np.ndarray, drows: int, dcols: int):
+        """cv::resize(img, Size(dcols, drows)) with INTER_LINEAR on uint8 pixels (H x W or H x W x C), bit-identical to cv2.resize."""
+        a = np.ascontiguousarray(img, dtype=np.uint8)
+        cn = 1 if a.ndim == 2 else a.shape[2]
+        out = np.zeros((drows, dcols) if a.ndim == 2 else (drows, dcols, cn), dtype=np.uint8)
+        self._check(lib().sift_b200_resize_linear_u8(self._h, _p(a), a.shape[0], a.shape[1], cn, _p(out), drows, dcols))
+        return out
+
+    def rgb2gray_u8(self, bgr: np.ndarray):
+        """cvtColor(COLOR_RGB2GRAY) applied to BGR bytes as the driver does (src/main.cpp:84)."""
+        a = np.ascontiguousarray(bgr, dtype=np.uint8)
+        assert a.ndim == 3 and a.shape[2] == 3
+        out = np.zeros(a.shape[:2], dtype=np.uint8)
+        self._check(lib().sift_b200_rgb2gray_u8(self._h, _p(a), a.shape[0], a.shape[1], _p(out)))
+        return out
+
+    def find_homography(self, src_xy, dst_xy, ransac_thresh: float = 3.0, max_iters: int = 2000):
+        """findHomography(src, dst, RANSAC).  Returns (H 3x3 float64 or None, inlier mask)."""
+        s = np.ascontiguousarray(src_xy, dtype=np.float32).reshape(-1, 2)
+        d = np.ascontiguousarray(dst_xy, dtype=np.float32).reshape(-1, 2)
+        assert len(s) == len(d)
+        H = np.zeros(9, dtype=np.float64)
+        mask = np.zeros(len(s), dtype=np.uint8)
+        n_in = C.c_int(0)
+        rc = self._check(lib().sift_b200_find_homography(self._h, _p(s), _p(d), len(s), C.c_double(ransac_thresh), max_iters, _p(H), _p(mask), C.byref(n_in)),
+                         allow=(ERR_TOO_SMALL,))
+        if rc == ERR_TOO_SMALL:
+            return None, mask.astype(bool)
+        return H.reshape(3, 3), mask.astype(bool)
 
     def match_knn2(self, query, train, norm: int = NORM_L1, ratio: float = 0.86, tensor_cores: bool = False, timing: bool = False):
         """BFMatcher(norm).knnMatch(k=2) + ratio test (src/main.cpp:25-40).  tensor_cores=True (NORM_L2 only) takes the tcgen05

@@ -605,6 +605,63 @@ int sift_b200_rgb2gray_u8_dev(SiftB200* h, const uint8_t* d_bgr, int n_frames, i
     return SIFT_B200_OK;
 }
 
+int sift_b200_resize_linear_u8(SiftB200* h, const uint8_t* src, int rows, int cols, int channels, uint8_t* dst, int drows, int dcols) {
+    if (!h || !src || !dst || rows < 1 || cols < 1 || drows < 1 || dcols < 1 || channels < 1 || channels > 4) return fail(SIFT_B200_ERR_ARG, "bad argument");
+    CUDA_TRY(cudaSetDevice(h->device));
+    const size_t sb = (size_t)rows * cols * channels, db = (size_t)drows * dcols * channels;
+    DevMem m_src, m_dst, m_tab;
+    CUDA_TRY(m_src.alloc(sb));
+    CUDA_TRY(m_dst.alloc(db));
+    CUDA_TRY(m_tab.alloc(resize_tab_bytes(drows, dcols)));
+    CUDA_TRY(cudaMemcpyAsync(m_src.p, src, sb, cudaMemcpyHostToDevice, h->stream));
+    h->launches += launch_resize_linear_u8(m_src.as<uint8_t>(), rows, cols, channels, m_dst.as<uint8_t>(), drows, dcols, m_tab.p, h->stream);
+    CUDA_TRY(cudaMemcpyAsync(dst, m_dst.p, db, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    CUDA_TRY(cudaGetLastError());
+    return SIFT_B200_OK;
+}
+
+int sift_b200_rgb2gray_u8(SiftB200* h, const uint8_t* bgr, int rows, int cols, uint8_t* gray) {
+    if (!h || !bgr || !gray || rows < 1 || cols < 1) return fail(SIFT_B200_ERR_ARG, "bad argument");
+    CUDA_TRY(cudaSetDevice(h->device));
+    const size_t n = (size_t)rows * cols;
+    DevMem m_src, m_dst;
+    CUDA_TRY(m_src.alloc(n * 3));
+    CUDA_TRY(m_dst.alloc(n));
+    CUDA_TRY(cudaMemcpyAsync(m_src.p, bgr, n * 3, cudaMemcpyHostToDevice, h->stream));
+    h->launches += launch_rgb2gray_u8(m_src.as<uint8_t>(), m_dst.as<uint8_t>(), n, h->stream);
+    CUDA_TRY(cudaMemcpyAsync(gray, m_dst.p, n, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    CUDA_TRY(cudaGetLastError());
+    return SIFT_B200_OK;
+}
+
+int sift_b200_find_homography(SiftB200* h, const float* src_xy, const float* dst_xy, int n, double ransac_thresh, int max_iters, double* H9_out,
+                              uint8_t* mask_out, int* n_inliers_out) {
+    if (!h || n < 0 || (n > 0 && (!src_xy || !dst_xy)) || !H9_out || !n_inliers_out) return fail(SIFT_B200_ERR_ARG, "bad argument");
+    *n_inliers_out = 0;
+    for (int i = 0; i < 9; ++i) H9_out[i] = 0;
+    if (n < 4) return fail(SIFT_B200_ERR_TOO_SMALL, "a homography needs at least 4 correspondences");
+    if (ransac_thresh <= 0) ransac_thresh = 3.0;  // cv::findHomography's default ransacReprojThreshold
+    const int n_hyp = max_iters > 0 ? (max_iters < 65536 ? max_iters : 65536) : 2000;  // cv::findHomography's default maxIters
+    CUDA_TRY(cudaSetDevice(h->device));
+    DevMem m_src, m_dst, m_work;
+    CUDA_TRY(m_src.alloc((size_t)n * 8));
+    CUDA_TRY(m_dst.alloc((size_t)n * 8));
+    CUDA_TRY(m_work.alloc(homography_work_bytes(n, n_hyp)));
+    CUDA_TRY(cudaMemcpyAsync(m_src.p, src_xy, (size_t)n * 8, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaMemcpyAsync(m_dst.p, dst_xy, (size_t)n * 8, cudaMemcpyHostToDevice, h->stream));
+    std::vector<uint8_t> mask(n);
+    const int nl = run_homography_ransac(m_src.as<float2>(), m_dst.as<float2>(), reinterpret_cast<const float2*>(src_xy), reinterpret_cast<const float2*>(dst_xy), n,
+                                         (float)ransac_thresh, n_hyp, 0x5eed1234u, m_work.p, H9_out, mask.data(), n_inliers_out, h->stream);
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    CUDA_TRY(cudaGetLastError());
+    if (nl < 0) return fail(SIFT_B200_ERR_TOO_SMALL, "no homography: every sampled quadruple was degenerate");
+    h->launches += nl;
+    if (mask_out) memcpy(mask_out, mask.data(), n);
+    return SIFT_B200_OK;
+}
+
 int sift_b200_upsample2x_dev(SiftB200* h, const float* d_src, int n_frames, int rows, int cols, float* d_dst, void* stream) {
     if (!h || !d_src || !d_dst || rows < 1 || cols < 1 || n_frames < 0) return fail(SIFT_B200_ERR_ARG, "bad argument");
     CUDA_TRY(cudaSetDevice(h->device));

@@ -114,6 +114,12 @@ int launch_describe(const PyrView& pv, const DetectBuf& db, int n_frames, SiftKe
 int launch_describe_given(const PyrView& pv, const SiftKeypoint* d_kps, int n, float* d_desc, int first_octave, int* d_err, DescParams* d_params,
                           cudaStream_t st);
 int launch_match(const float* d_q, int nq, const float* d_t, int nt, int norm, float* d_dist, int32_t* d_idx, cudaStream_t st);
+// the driver's front and back ends (driver.cu): fixed-point bilinear resize of 8-bit images, RANSAC homography
+size_t resize_tab_bytes(int drows, int dcols);
+int launch_resize_linear_u8(const uint8_t* d_src, int srows, int scols, int cn, uint8_t* d_dst, int drows, int dcols, void* d_tab, cudaStream_t st);
+size_t homography_work_bytes(int n, int n_hyp);
+int run_homography_ransac(const float2* d_src, const float2* d_dst, const float2* h_src, const float2* h_dst, int n, float thresh, int n_hyp, uint32_t seed,
+                          void* d_work, double* H9, uint8_t* mask, int* n_inliers, cudaStream_t st);
 // tcgen05 L2 matcher: bf16 hi/lo operand tiles -> tensor-core shortlists -> exact fp64 re-rank (match_tc.cu)
 size_t match_tc_scratch_bytes(int nq, int nt);
 int launch_match_tc(const float* d_q, int nq, const float* d_t, int nt, void* d_scratch, float* d_dist, int32_t* d_idx, cudaStream_t st);

@@ -23,7 +23,7 @@ struct Workspace {
 };
 Workspace g_ws;
 
-[[noreturn]] void raise(const char* what) { throw cv::Exception(std::string(what) + ": " + sift_b200_last_error()); }
+[[noreturn]] void raise(const char* what) { CV_Error(cv::Error::StsError, std::string(what) + ": " + sift_b200_last_error()); }
 
 int device_ordinal() {
     const char* e = std::getenv("SIFT_B200_DEVICE");
@@ -118,14 +118,14 @@ void SIFT_NCL(InputArray image, std::vector<KeyPoint>& keypoints, OutputArray de
 }
 
 void SITF_BuildIn_OpenCV(InputArray image, std::vector<KeyPoint>& keypoints, OutputArray descriptors) {
-#ifdef SIFT_B200_WITH_XFEATURES2D
+#if defined(SIFT_B200_WITH_XFEATURES2D) && defined(SIFT_B200_HAVE_XFEATURES2D)
     Ptr<SIFT> detector = SIFT::create();
     Mat mask;
     detector->detectAndCompute(image, mask, keypoints, descriptors, false);
 #else
     (void)image; (void)keypoints; (void)descriptors;
-    throw cv::Exception("SITF_BuildIn_OpenCV: third-party CPU SIFT (opencv_contrib xfeatures2d) is not part of this library; "
-                        "rebuild with -DSIFT_B200_WITH_XFEATURES2D against opencv_contrib to forward to it");
+    CV_Error(cv::Error::StsError, "SITF_BuildIn_OpenCV: third-party CPU SIFT (opencv_contrib xfeatures2d) is not part of this library; "
+                                  "rebuild with -DSIFT_B200_WITH_XFEATURES2D against opencv_contrib to forward to it");
 #endif
 }
 

@@ -48,13 +48,26 @@ def test_no_cpu_fallback(pkg):
 
 
 def test_product_never_imports_the_oracle(ge):
-    """oracle/ is test infrastructure: nothing under sift-gpu_b200/ or include/ may mention it."""
+    """oracle/ is test infrastructure: nothing under sift-gpu_b200/ or include/ -- sources AND build recipes -- may mention it, and the
+    OpenCV stand-in the product builds against (third_party/cvshim) may reach oracle headers only behind CVSHIM_ORACLE_PRIMS, a macro no
+    product recipe defines."""
     bad = []
     for base in (ge.PKG_DIR, os.path.join(ge.ROOT, "include")):
         for dp, _, fs in os.walk(base):
             for f in fs:
-                if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".hpp")):
+                if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".hpp", ".mk")) or f == "Makefile":
                     txt = open(os.path.join(dp, f), errors="ignore").read()
-                    if re.search(r"liboracle|oracle\.py|sift_oracle|load_oracle|#include\s+\"oracle", txt):
+                    if f == "Makefile" or f.endswith(".mk"):  # recipes: no include / library path, no macro that opens the oracle door
+                        txt = "\n".join(l for l in txt.splitlines() if not l.lstrip().startswith("#"))
+                        if re.search(r"oracle|CVSHIM_ORACLE_PRIMS", txt):
+                            bad.append(os.path.join(dp, f))
+                    elif re.search(r"liboracle|oracle\.py|sift_oracle|load_oracle|#include\s+[\"<]oracle|CVSHIM_ORACLE_PRIMS", txt):
                         bad.append(os.path.join(dp, f))
     assert not bad, bad
+    shim = os.path.join(ge.ROOT, "third_party", "cvshim")
+    for dp, _, fs in os.walk(shim):
+        for f in fs:
+            txt = open(os.path.join(dp, f), errors="ignore").read()
+            for m in re.finditer(r'#include\s+"(oracle[^"]*)"', txt):
+                head = txt[: m.start()]
+                assert head.count("#ifdef CVSHIM_ORACLE_PRIMS") > head.count("#endif") - head.count("#ifndef") - head.count("#if "), (f, m.group(1))

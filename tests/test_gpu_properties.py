@@ -165,7 +165,7 @@ def test_launches_are_counted(pkg, synth):
     s = pkg.Sift(128, 128, max_batch=1, max_kp_per_frame=1024)
     n0 = s.launch_count()
     s.detect_describe(synth.recipe_s(128, 128, seed=4))
-    assert s.launch_count() - n0 == 12  # base blur, 5 octaves, gradient maps, extrema scan, refine, orientation, order+scan, descriptors
+    assert s.launch_count() - n0 == 13  # base blur, 5 octaves, gradient maps, extrema scan, refine, orientation, order+scan, descriptor prep, descriptors
     s.close()
 
 
