@@ -158,6 +158,12 @@ class Sift:
         n, rows, cols, _ = d_bgr.shape
         self._check(lib().sift_b200_rgb2gray_u8_dev(self._h, C.c_void_p(d_bgr.data_ptr()), n, rows, cols, C.c_void_p(d_gray.data_ptr()), C.c_void_p(stream)))
 
+    def upsample2x_dev(self, d_src, d_dst, stream: int = 0):
+        """Config 3 front end on device tensors: float32 [N,H,W] -> float32 [N,2H,2W] (cv::resize INTER_LINEAR semantics), asynchronous."""
+        n, rows, cols = d_src.shape
+        assert tuple(d_dst.shape) == (n, 2 * rows, 2 * cols) and d_src.is_contiguous() and d_dst.is_contiguous()
+        self._check(lib().sift_b200_upsample2x_dev(self._h, C.c_void_p(d_src.data_ptr()), n, rows, cols, C.c_void_p(d_dst.data_ptr()), C.c_void_p(stream)))
+
     def detect_describe_batch_host_u8_ptr(self, imgs_ptr: int, n: int, rows: int, cols: int, kp_ptr: int, desc_ptr: int, counts_ptr: int, cap: int):
         return self._check(lib().sift_b200_detect_describe_batch_host_u8(self._h, C.c_void_p(imgs_ptr), n, rows, cols, C.c_void_p(kp_ptr), C.c_void_p(desc_ptr),
                                                                          C.c_void_p(counts_ptr), cap), allow=(ERR_CAPACITY,))
