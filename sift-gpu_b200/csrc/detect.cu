@@ -217,7 +217,10 @@ __global__ void __launch_bounds__(128) refine_kernel(const __grid_constant__ Pyr
 // a level are issued before any arithmetic (memory-level parallelism: the kernel is bandwidth/latency bound, not compute
 // bound); dx comes from two shuffles per row (the strip's left/right neighbours are fetched by lanes 0 and 31), dy from the
 // rows in registers.
-constexpr int GR_COLS = 32, GR_ROWS = 8, GR_WARPS = 4;
+#ifndef GR_MIN_CTAS
+#define GR_MIN_CTAS 8
+#endif
+constexpr int GR_COLS = 32, GR_ROWS = kGradRows, GR_WARPS = 4;
 
 template <int NL>
 __device__ __forceinline__ void gradient_strip(const float* const (&G)[NL], float2* const (&MO)[NL], int rows, int cols, int pitch, int x, int y0, int y1,
@@ -246,8 +249,10 @@ __device__ __forceinline__ void gradient_strip(const float* const (&G)[NL], floa
     }
 }
 
-// full = 0: levels 1,2 (the fused pipeline); full = 1: all five levels (stage-level API)
-__global__ void __launch_bounds__(GR_WARPS * 32, 8) gradient_kernel(const __grid_constant__ PyrView pv, int full) {
+// FULL = false: levels 1,2 (the fused pipeline); FULL = true: all five levels (stage-level API).  Two kernels, so that the hot one is
+// register-allocated on its own (as one kernel with a run-time switch the two-level path spilled).
+template <bool FULL>
+__global__ void __launch_bounds__(GR_WARPS * 32, FULL ? 4 : GR_MIN_CTAS) gradient_kernel(const __grid_constant__ PyrView pv) {
     const int lane = threadIdx.x & 31;
     const int strip = blockIdx.x * GR_WARPS + (threadIdx.x >> 5);
     if (strip >= pv.total_grad_tiles) return;
@@ -262,7 +267,7 @@ __global__ void __launch_bounds__(GR_WARPS * 32, 8) gradient_kernel(const __grid
     const int y0 = 1 + (t / ov.grad_tiles_x) * GR_ROWS;                     // only 0 < y < rows-1, 0 < x < cols-1 is ever sampled
     const int y1 = min(y0 + GR_ROWS, rows - 1);
     const size_t foff = (size_t)blockIdx.y * ov.frame_stride;
-    if (!full) {
+    if (!FULL) {
         const float* const G[2] = {ov.G[1] + foff, ov.G[2] + foff};
         float2* const MO[2] = {ov.MO[1] + foff, ov.MO[2] + foff};
         gradient_strip<2>(G, MO, rows, cols, pitch, x, y0, y1, lane);
@@ -486,8 +491,9 @@ int launch_extrema(const PyrView& pv, const DetectBuf& db, int n_frames, cudaStr
 }
 
 int launch_gradient(const PyrView& pv, int n_frames, cudaStream_t st) {
-    const int full = pv.oct[0].MO[0] != nullptr;
-    gradient_kernel<<<dim3((pv.total_grad_tiles + GR_WARPS - 1) / GR_WARPS, n_frames), GR_WARPS * 32, 0, st>>>(pv, full);
+    const dim3 grid((pv.total_grad_tiles + GR_WARPS - 1) / GR_WARPS, n_frames);
+    if (pv.oct[0].MO[0] != nullptr) gradient_kernel<true><<<grid, GR_WARPS * 32, 0, st>>>(pv);
+    else gradient_kernel<false><<<grid, GR_WARPS * 32, 0, st>>>(pv);
     return 1;
 }
 

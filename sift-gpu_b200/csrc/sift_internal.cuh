@@ -22,6 +22,10 @@ constexpr int kMaxInterpSteps = 5; // src/sift.cpp:24
 constexpr int kOriBins = 36;       // src/sift.cpp:27
 constexpr int kMaxPeaks = 18;      // strict local maxima of a 36-bin circular histogram
 constexpr int kMaxRadius = 18;     // floor(3*sig[4]) = floor(3*6.196774)
+#ifndef GR_ROWS_
+#define GR_ROWS_ 8
+#endif
+constexpr int kGradRows = GR_ROWS_; // rows of a gradient strip (32 aligned columns x kGradRows rows per warp, detect.cu)
 
 struct OctaveView {
     float* G[kNumScales];     // Gaussian levels (G[3], G[4] may be null in the fused pipeline)
