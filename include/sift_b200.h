@@ -42,7 +42,10 @@ typedef struct SiftB200 SiftB200; /* opaque handle: device workspace for up to m
 
 enum {
     SIFT_B200_OK = 0,
-    SIFT_B200_ERR_CAPACITY = 1, /* more keypoints than `cap`: outputs truncated to cap, *n_out = true count */
+    SIFT_B200_ERR_CAPACITY = 1, /* more keypoints than `cap`: the first cap records (reference order) are written, *n_out = true count.
+                                 * If an INTERNAL list overflowed (more than max(16384, 4*max_kp, pixels/64) raw extrema or more than max_kp
+                                 * refined points in one frame) the true count is unknown: *n_out = max_kp_per_frame + 1, and only the records
+                                 * the kernels produced are written -- host buffers beyond them are left untouched */
     SIFT_B200_ERR_ARG = 2,
     SIFT_B200_ERR_CUDA = 3,      /* no device / CUDA failure: sift_b200_last_error() has the text */
     SIFT_B200_ERR_TOO_SMALL = 4, /* an octave would be empty (reference: cv::resize throws, src/sift.cpp:254) */

@@ -197,11 +197,14 @@ int copy_levels(const PyrView& pv, bool gauss, int per, float* packed, bool to_d
     return SIFT_B200_OK;
 }
 
-int alloc_detectbuf(DetectBuf& db, size_t F, int cap_r) {
+int alloc_detectbuf(DetectBuf& db, size_t F, int cap_r, size_t max_pixels) {
     db.cap_r = cap_r;
     db.cap_r_pow2 = next_pow2(db.cap_r);
     const size_t C = db.cap_r;
-    db.cap_c = 4 * db.cap_r < 16384 ? 16384 : 4 * db.cap_r;  // extrema before refinement (20-85 % survive)
+    // extrema before refinement: 20-85 % survive, and a frame of faint texture has many more candidates than keypoints:
+    // the list also scales with the image area (one candidate per 64 pixels, twenty times the densest frame seen)
+    db.cap_c = 4 * db.cap_r < 16384 ? 16384 : 4 * db.cap_r;
+    if ((size_t)db.cap_c < max_pixels / 64) db.cap_c = (int)(max_pixels / 64);
     CUDA_TRY(cudaMalloc((void**)&db.cand, F * (size_t)db.cap_c * sizeof(uint32_t)));
     CUDA_TRY(cudaMalloc((void**)&db.n_cand, F * sizeof(int)));
     CUDA_TRY(cudaMalloc((void**)&db.refined, F * C * sizeof(Refined)));
@@ -225,7 +228,7 @@ void free_detectbuf(DetectBuf& db) {
 int ensure_lane2(SiftB200* h) {
     if (h->ws2) return SIFT_B200_OK;
     CUDA_TRY(cudaMalloc((void**)&h->ws2, h->ws_floats * sizeof(float)));
-    int rc = alloc_detectbuf(h->db2, h->max_batch, h->cap_kp);
+    int rc = alloc_detectbuf(h->db2, h->max_batch, h->cap_kp, (size_t)h->max_rows * h->max_cols);
     if (rc) return rc;
     CUDA_TRY(cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
     CUDA_TRY(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
@@ -354,12 +357,12 @@ static int create_impl(SiftB200* h) {
     h->ws_floats = frame_floats(max_rows, max_cols, 5, 11) * max_batch;  // G0..G2, D0..D3, 2 x float2 gradient maps
     CUDA_TRY(cudaMalloc((void**)&h->ws, h->ws_floats * sizeof(float)));
     const size_t F = max_batch;
-    if (int rc_db = alloc_detectbuf(h->db, F, max_kp_per_frame)) return rc_db;
+    if (int rc_db = alloc_detectbuf(h->db, F, max_kp_per_frame, (size_t)max_rows * max_cols)) return rc_db;
     if (const char* e = getenv("SIFT_B200_LANES")) h->lanes = atoi(e);
     if (const char* e = getenv("SIFT_B200_TAPER")) h->taper = atoi(e) != 0;
     if (const char* e = getenv("SIFT_B200_EXACT_PYRAMID")) h->exact_pyramid = atoi(e) != 0;
     CUDA_TRY(cudaMalloc((void**)&h->d_counts, F * sizeof(int)));
-    CUDA_TRY(cudaMallocHost((void**)&h->h_counts, F * sizeof(int)));
+    CUDA_TRY(cudaMallocHost((void**)&h->h_counts, 2 * F * sizeof(int)));  // [F] reported counts | [F] records actually written
     for (auto& e : h->ev) CUDA_TRY(cudaEventCreate(&e));
     float sig[5];
     pipeline_sigmas(sig);
@@ -435,7 +438,7 @@ static int ensure_pipeline(SiftB200* h) {
     CUDA_TRY(cudaMalloc((void**)&h->d_kp2, F * (size_t)h->cap_kp * sizeof(SiftKeypoint)));
     CUDA_TRY(cudaMalloc((void**)&h->d_desc2, F * (size_t)h->cap_kp * 128 * sizeof(float)));
     CUDA_TRY(cudaMalloc((void**)&h->d_counts2, F * sizeof(int)));
-    CUDA_TRY(cudaMallocHost((void**)&h->h_counts2, F * sizeof(int)));
+    CUDA_TRY(cudaMallocHost((void**)&h->h_counts2, 2 * F * sizeof(int)));
     CUDA_TRY(cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking));
     for (int b = 0; b < 3; ++b) {
@@ -525,9 +528,10 @@ static int batch_host_run(SiftB200* h, const void* imgs_v, int elem, int n_frame
         const int b = k & 1, f0 = first[k], nf = plan[k];
         CUDA_TRY(cudaEventSynchronize(h->ev_cnt[b]));
         for (int f = 0; f < nf; ++f) {
-            int n = h_cnt[b][f];
-            counts_out[f0 + f] = n;
-            if (n > cap) { n = cap; status = SIFT_B200_ERR_CAPACITY; }
+            int n = h_cnt[b][h->max_batch + f];  // records the kernels wrote (differs from the reported count when an internal list overflowed)
+            counts_out[f0 + f] = h_cnt[b][f];
+            if (h_cnt[b][f] > cap) status = SIFT_B200_ERR_CAPACITY;
+            if (n > cap) n = cap;
             if (n > 0) {
                 CUDA_TRY(cudaMemcpyAsync(kp_out + (size_t)(f0 + f) * cap, d_kp[b] + (size_t)f * cap, n * sizeof(SiftKeypoint), cudaMemcpyDeviceToHost, h->s_out));
                 CUDA_TRY(cudaMemcpyAsync(desc_out + (size_t)(f0 + f) * cap * 128, d_desc[b] + (size_t)f * cap * 128, (size_t)n * 128 * sizeof(float),
@@ -551,6 +555,7 @@ static int batch_host_run(SiftB200* h, const void* imgs_v, int elem, int n_frame
         if (k >= 1 && (rc = flush(k - 1))) return rc;
         CUDA_TRY(cudaStreamWaitEvent(h->s_out, h->ev_comp[ib], 0));
         CUDA_TRY(cudaMemcpyAsync(h_cnt[b], d_cnt[b], nf * sizeof(int), cudaMemcpyDeviceToHost, h->s_out));
+        CUDA_TRY(cudaMemcpyAsync(h_cnt[b] + h->max_batch, (two && b ? h->db2 : h->db).n_kp, nf * sizeof(int), cudaMemcpyDeviceToHost, h->s_out));
         CUDA_TRY(cudaEventRecord(h->ev_cnt[b], h->s_out));
     }
     if (n_chunks > 0 && (rc = flush(n_chunks - 1))) return rc;
@@ -571,6 +576,17 @@ int sift_b200_detect_describe_batch_host_u8(SiftB200* h, const uint8_t* imgs, in
     return batch_host_impl(h, imgs, 1, n_frames, rows, cols, kp_out, desc_out, counts_out, cap);
 }
 
+// count reported to the caller (true count, or the overflow sentinel cap_r + 1) and number of records the kernels really wrote for frame 0
+// of lane 0; synchronises the handle's stream
+static int fetch_counts(SiftB200* h, int* reported, int* written) {
+    CUDA_TRY(cudaMemcpyAsync(h->h_counts, h->d_counts, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaMemcpyAsync(h->h_counts + 1, h->db.n_kp, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    *reported = h->h_counts[0];
+    *written = h->h_counts[1];
+    return SIFT_B200_OK;
+}
+
 int sift_b200_detect_describe(SiftB200* h, const float* img, int rows, int cols, size_t row_stride_bytes, SiftKeypoint* kp_out, float* desc_out, int cap,
                               int* n_out) {
     int rc = check_dims(h, rows, cols);
@@ -583,12 +599,12 @@ int sift_b200_detect_describe(SiftB200* h, const float* img, int rows, int cols,
     CUDA_TRY(cudaMemcpy2DAsync(h->d_img, (size_t)cols * 4, img, row_stride_bytes, (size_t)cols * 4, rows, cudaMemcpyHostToDevice, h->stream));
     rc = run_pipeline(h, h->d_img, nullptr, 1, rows, cols, h->d_kp, h->d_desc, h->d_counts, cap, h->stream);
     if (rc) return rc;
-    CUDA_TRY(cudaMemcpyAsync(h->h_counts, h->d_counts, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-    CUDA_TRY(cudaStreamSynchronize(h->stream));
-    int n = h->h_counts[0];
-    *n_out = n;
+    int n_rep = 0, n = 0;
+    if ((rc = fetch_counts(h, &n_rep, &n))) return rc;
+    *n_out = n_rep;
     int status = SIFT_B200_OK;
-    if (n > cap) { n = cap; status = fail(SIFT_B200_ERR_CAPACITY, "keypoint capacity exceeded: outputs truncated"); }
+    if (n_rep > cap) status = fail(SIFT_B200_ERR_CAPACITY, "keypoint capacity exceeded: outputs truncated");
+    if (n > cap) n = cap;
     if (n > 0) {
         CUDA_TRY(cudaMemcpyAsync(kp_out, h->d_kp, n * sizeof(SiftKeypoint), cudaMemcpyDeviceToHost, h->stream));
         CUDA_TRY(cudaMemcpyAsync(desc_out, h->d_desc, (size_t)n * 128 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
@@ -685,12 +701,12 @@ int sift_b200_detect_describe_up2(SiftB200* h, const float* img, int rows, int c
     if (upsampled_out) CUDA_TRY(cudaMemcpyAsync(upsampled_out, h->d_img, (size_t)rows * cols * 16, cudaMemcpyDeviceToHost, h->stream));
     rc = run_pipeline(h, h->d_img, nullptr, 1, 2 * rows, 2 * cols, h->d_kp, h->d_desc, h->d_counts, cap, h->stream);
     if (rc) { cudaStreamSynchronize(h->stream); return rc; }
-    CUDA_TRY(cudaMemcpyAsync(h->h_counts, h->d_counts, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-    CUDA_TRY(cudaStreamSynchronize(h->stream));
-    int n = h->h_counts[0];
-    *n_out = n;
+    int n_rep = 0, n = 0;
+    if ((rc = fetch_counts(h, &n_rep, &n))) return rc;
+    *n_out = n_rep;
     int status = SIFT_B200_OK;
-    if (n > cap) { n = cap; status = fail(SIFT_B200_ERR_CAPACITY, "keypoint capacity exceeded: outputs truncated"); }
+    if (n_rep > cap) status = fail(SIFT_B200_ERR_CAPACITY, "keypoint capacity exceeded: outputs truncated");
+    if (n > cap) n = cap;
     if (n > 0) {
         CUDA_TRY(cudaMemcpy(kp_out, h->d_kp, n * sizeof(SiftKeypoint), cudaMemcpyDeviceToHost));
         CUDA_TRY(cudaMemcpy(desc_out, h->d_desc, (size_t)n * 128 * sizeof(float), cudaMemcpyDeviceToHost));
@@ -801,12 +817,12 @@ int sift_b200_find_scale_space_extrema(SiftB200* h, const float* gpyr, const flo
     h->launches += launch_order_scan(h->db, 1, h->d_counts, h->stream);
     // the descriptor kernel also emits the keypoint records; descriptors land in staging and are dropped
     h->launches += launch_describe(pv, h->db, 1, h->d_kp, h->d_desc, cap, h->stream);
-    CUDA_TRY(cudaMemcpyAsync(h->h_counts, h->d_counts, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-    CUDA_TRY(cudaStreamSynchronize(h->stream));
-    int n = h->h_counts[0];
-    *n_out = n;
+    int n_rep = 0, n = 0;
+    if ((rc = fetch_counts(h, &n_rep, &n))) return rc;
+    *n_out = n_rep;
     int status = SIFT_B200_OK;
-    if (n > cap) { n = cap; status = fail(SIFT_B200_ERR_CAPACITY, "keypoint capacity exceeded: outputs truncated"); }
+    if (n_rep > cap) status = fail(SIFT_B200_ERR_CAPACITY, "keypoint capacity exceeded: outputs truncated");
+    if (n > cap) n = cap;
     if (n > 0) CUDA_TRY(cudaMemcpy(kp_out, h->d_kp, n * sizeof(SiftKeypoint), cudaMemcpyDeviceToHost));
     CUDA_TRY(cudaGetLastError());
     return status;

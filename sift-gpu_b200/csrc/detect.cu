@@ -471,8 +471,9 @@ __global__ void __launch_bounds__(SORT_THREADS) order_scan_kernel(const DetectBu
     if (tid == 0) {
         int total = s_carry;
         db.n_kp[f] = total;  // what the descriptor stage iterates over
-        // a full candidate / refined list means keypoints were dropped: report a count above any admissible cap
-        if (db.n_refined[f] > db.cap_r || db.n_cand[f] > db.cap_c) total = max(total, db.cap_r + 1);
+        // a full candidate / refined list means keypoints were dropped and the true count is unknown: report the sentinel cap_r + 1 (above
+        // any admissible cap); n_kp keeps the number of records that do exist
+        if (db.n_refined[f] > db.cap_r || db.n_cand[f] > db.cap_c) total = db.cap_r + 1;
         counts_out[f] = total;
     }
 }

@@ -63,21 +63,27 @@ __device__ bool homography_from4(const float2* s, const float2* d, double* H) {
         double r1[9] = {0, 0, 0, x, y, 1, -x * Y, -y * Y, Y};
         for (int j = 0; j < 9; ++j) { A[2 * i][j] = r0[j]; A[2 * i + 1][j] = r1[j]; }
     }
-    for (int c = 0; c < 8; ++c) {
+#pragma unroll 1
+    for (int c = 0; c < 8; ++c) {  // rolled on purpose: one lane per hypothesis runs this, code size matters more than speed
         int piv = c;
+#pragma unroll 1
         for (int r = c + 1; r < 8; ++r)
             if (fabs(A[r][c]) > fabs(A[piv][c])) piv = r;
         if (fabs(A[piv][c]) < 1e-12) return false;
         if (piv != c)
             for (int j = c; j < 9; ++j) { const double t = A[c][j]; A[c][j] = A[piv][j]; A[piv][j] = t; }
         const double inv = 1.0 / A[c][c];
+#pragma unroll 1
         for (int r = c + 1; r < 8; ++r) {
             const double f = A[r][c] * inv;
+#pragma unroll 1
             for (int j = c; j < 9; ++j) A[r][j] -= f * A[c][j];
         }
     }
+#pragma unroll 1
     for (int r = 7; r >= 0; --r) {
         double v = A[r][8];
+#pragma unroll 1
         for (int j = r + 1; j < 8; ++j) v -= A[r][j] * H[j];
         H[r] = v / A[r][r];
     }
@@ -88,10 +94,14 @@ __device__ bool homography_from4(const float2* s, const float2* d, double* H) {
 // OpenCV's sample check for homographies (haveCollinearPoints + the orientation test of checkSubset): reject a sample with three
 // nearly collinear points in either image, or one whose two point quadruples are oriented differently.
 __device__ bool sample_ok(const float2* s, const float2* d) {
+#pragma unroll 1
     for (int pass = 0; pass < 2; ++pass) {
         const float2* p = pass ? d : s;
+#pragma unroll 1
         for (int i = 0; i < 4; ++i)
+#pragma unroll 1
             for (int j = i + 1; j < 4; ++j)
+#pragma unroll 1
                 for (int k = j + 1; k < 4; ++k) {
                     const double dx1 = p[j].x - p[i].x, dy1 = p[j].y - p[i].y, dx2 = p[k].x - p[i].x, dy2 = p[k].y - p[i].y;
                     if (fabs(dx2 * dy1 - dy2 * dx1) <= 1.1920928955078125e-7 * (fabs(dx1) + fabs(dy1) + fabs(dx2) + fabs(dy2))) return false;
@@ -125,6 +135,7 @@ __global__ void __launch_bounds__(128) homography_hypotheses_kernel(const float2
     if (lane == 0) {
         float2 s[4], d[4];
         int idx[4];
+#pragma unroll 1
         for (int attempt = 0; attempt < 16 && !ok; ++attempt) {
             uint32_t ctr = seed ^ mix32((uint32_t)k * 64u + (uint32_t)attempt);
             bool distinct = true;

@@ -47,6 +47,22 @@ def test_no_cpu_fallback(pkg):
     assert pkg.lib().sift_b200_create(C.byref(h), 8, 8, 1, 16, 0) == pkg.ERR_ARG  # argument check precedes device probing
 
 
+def test_image_size_limit_is_checked_before_anything_else(pkg):
+    """Extrema candidates are packed as o<<27 | layer<<26 | row<<13 | col (detect.cu), so rows and cols must stay below 8192: the limit
+    is an argument error at create time (and again per call), never a silent wrap of the 13-bit fields."""
+    h = C.c_void_p()
+    lib = pkg.lib()
+    for rows, cols in ((8192, 64), (64, 8192), (1 << 20, 1 << 20), (15, 64), (64, 15)):
+        assert lib.sift_b200_create(C.byref(h), rows, cols, 1, 16, 0) == pkg.ERR_ARG, (rows, cols)
+    assert b"8192" in lib.sift_b200_last_error()
+    assert lib.sift_b200_create(C.byref(h), 8191, 8191, 0, 16, 0) == pkg.ERR_ARG  # batch < 1
+    assert lib.sift_b200_create(C.byref(h), 8191, 8191, 1, 0, 0) == pkg.ERR_ARG  # capacity < 1
+    import torch
+
+    if not torch.cuda.is_available():  # the largest admissible size passes the argument check and only then fails for want of a device
+        assert lib.sift_b200_create(C.byref(h), 8191, 8191, 1, 16, 0) == pkg.ERR_CUDA
+
+
 def test_product_never_imports_the_oracle(ge):
     """oracle/ is test infrastructure: nothing under sift-gpu_b200/ or include/ -- sources AND build recipes -- may mention it, and the
     OpenCV stand-in the product builds against (third_party/cvshim) may reach oracle headers only behind CVSHIM_ORACLE_PRIMS, a macro no

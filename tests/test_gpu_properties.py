@@ -161,6 +161,34 @@ def test_edge_cases_and_errors(pkg, oracle, synth):
     s.close()
 
 
+def test_internal_list_overflow_contract(pkg, synth):
+    """A frame with more refined extrema than the handle's max_kp_per_frame: the true keypoint count is unknown, so the call reports
+    max_kp + 1 with ERR_CAPACITY, writes only the records the kernels produced (all of them valid, in reference order) and leaves the
+    rest of the caller's buffers untouched (include/sift_b200.h)."""
+    import ctypes as C
+
+    img = synth.recipe_s(640, 360, seed=100)
+    big = pkg.Sift(360, 640, max_batch=1, max_kp_per_frame=4096)
+    kp_all, desc_all = big.detect_describe(img)
+    big.close()
+    assert len(kp_all) > 200
+    cap = 64
+    s = pkg.Sift(360, 640, max_batch=1, max_kp_per_frame=cap)
+    kps = np.zeros(cap + 8, dtype=pkg.KP_DTYPE)
+    desc = np.full((cap + 8, 128), -7.0, dtype=np.float32)
+    n = C.c_int(0)
+    rc = pkg.lib().sift_b200_detect_describe(s._h, img.ctypes.data_as(C.c_void_p), 360, 640, C.c_size_t(640 * 4), kps.ctypes.data_as(C.c_void_p),
+                                             desc.ctypes.data_as(C.c_void_p), cap, C.byref(n))
+    assert rc == pkg.ERR_CAPACITY and n.value == cap + 1
+    written = int((desc[:, 0] != -7.0).sum())
+    assert 0 < written <= cap and np.all(desc[written:] == -7.0)
+    # every written row is a real descriptor of this image (unit norm) belonging to one of its keypoints
+    assert np.allclose(np.linalg.norm(desc[:written], axis=1), 1.0, atol=1e-5)
+    all_xy = {(float(k["x"]), float(k["y"])) for k in kp_all}
+    assert all((float(k["x"]), float(k["y"])) in all_xy for k in kps[:written])
+    s.close()
+
+
 def test_launches_are_counted(pkg, synth):
     s = pkg.Sift(128, 128, max_batch=1, max_kp_per_frame=1024)
     n0 = s.launch_count()

@@ -5,8 +5,10 @@ import csv, json, re, subprocess, sys, collections
 
 
 def short(name):
-    m = re.search(r"(\w+)\(", name.replace("unnamed>::", ""))
-    return m.group(1) if m else name[:40]
+    """siftb200::<unnamed>::gradient_kernel<false>(PyrView) -> gradient_kernel"""
+    head = re.sub(r"<[^<>]*>", "", name.split("(")[0])  # drop template arguments and the <unnamed> namespace
+    head = re.sub(r"<[^<>]*>", "", head)
+    return head.split("::")[-1].split()[-1] if head.strip() else name[:40]
 
 
 def launches(path, out, title):
