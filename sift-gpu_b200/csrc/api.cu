@@ -112,8 +112,8 @@ int make_view(float* base, int rows, int cols, int n_oct, int n_frames, bool ful
         for (int i = 0; i < kNumScales; ++i) {
             if (i == 1 || i == 2 || full) { v.MO[i] = reinterpret_cast<float2*>(p); p += 2 * lvl; } else v.MO[i] = nullptr;
         }
-        // gradient strips: 32 aligned columns x kGradRows rows over rows [1, rows-1)  (detect.cu)
-        v.grad_tiles_x = cols > 2 ? (cols + 31) / 32 : 0;
+        // gradient strips: kGradCols aligned columns x kGradRows rows over rows [1, rows-1)  (detect.cu)
+        v.grad_tiles_x = cols > 2 ? (cols + kGradCols - 1) / kGradCols : 0;
         v.grad_tile_base = gtiles;
         gtiles += (cols > 2 && rows > 2) ? v.grad_tiles_x * ((rows - 2 + kGradRows - 1) / kGradRows) : 0;
         // extrema strips: 30 x 16 outputs over the interior [5, rows-5) x [5, cols-5)  (detect.cu)

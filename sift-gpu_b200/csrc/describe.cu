@@ -191,23 +191,33 @@ __device__ __forceinline__ void walk_slab(const float2* __restrict__ mo, const f
         const float rf = rbin - r0f;
         // trilinear split in the reference's operation order (:656-662)
         const float v_r1 = mag * rf, v_r0 = mag - v_r1;
-        auto rmw = [&](float* q, float add, bool st_) {
-            const float t = *q + add;
-            if (st_) *q = t;
-        };
-        // buffer 0 = cell-row r0, buffer 1 = cell-row r0+1: every address is one of two registers plus an immediate
-        float* const pA = priv + cA, * const pB = priv + cB;
+        // buffer 0 = cell-row r0, buffer 1 = cell-row r0+1: every address is one of two registers plus an immediate.  All loads are issued before
+        // the first store (one shared-memory latency per sample instead of four: the compiler cannot prove pA != pB and would otherwise keep
+        // the read-modify-writes of the two cells in program order).  pA == pB only happens for clamped out-of-grid cells, and then at most
+        // one of the two is stored, so loading everything first reads the same values.
+        float* const pA = priv + cA + oA, * const pB = priv + cB + oA;
+        constexpr int OB = PB == 9 ? 32 : 0;
+        float* const pAo = PB == 9 ? pA : priv + cA + oB, * const pBo = PB == 9 ? pB : priv + cB + oB;
+        float tA0 = 0.f, tA1 = 0.f, tB0 = 0.f, tB1 = 0.f, uA0 = 0.f, uA1 = 0.f, uB0 = 0.f, uB1 = 0.f;
+        if (HAS_LO) { tA0 = pA[0]; tA1 = pAo[OB]; tB0 = pB[0]; tB1 = pBo[OB]; }
+        if (HAS_HI) { uA0 = pA[ROWBUF]; uA1 = pAo[ROWBUF + OB]; uB0 = pB[ROWBUF]; uB1 = pBo[ROWBUF + OB]; }
         if (HAS_LO) {
             const float v_rc01 = v_r0 * cf, v_rc00 = v_r0 - v_rc01;
-            float v1;
-            v1 = v_rc00 * obin; rmw(pA + oA, v_rc00 - v1, stA); rmw(pA + oB, v1, stA);
-            v1 = v_rc01 * obin; rmw(pB + oA, v_rc01 - v1, stB); rmw(pB + oB, v1, stB);
+            const float vA = v_rc00 * obin, vB = v_rc01 * obin;
+            tA0 += v_rc00 - vA; tA1 += vA; tB0 += v_rc01 - vB; tB1 += vB;
         }
         if (HAS_HI) {
             const float v_rc11 = v_r1 * cf, v_rc10 = v_r1 - v_rc11;
-            float v1;
-            v1 = v_rc10 * obin; rmw(pA + ROWBUF + oA, v_rc10 - v1, stA); rmw(pA + ROWBUF + oB, v1, stA);
-            v1 = v_rc11 * obin; rmw(pB + ROWBUF + oA, v_rc11 - v1, stB); rmw(pB + ROWBUF + oB, v1, stB);
+            const float vA = v_rc10 * obin, vB = v_rc11 * obin;
+            uA0 += v_rc10 - vA; uA1 += vA; uB0 += v_rc11 - vB; uB1 += vB;
+        }
+        if (stA) {
+            if (HAS_LO) { pA[0] = tA0; pAo[OB] = tA1; }
+            if (HAS_HI) { pA[ROWBUF] = uA0; pAo[ROWBUF + OB] = uA1; }
+        }
+        if (stB) {
+            if (HAS_LO) { pB[0] = tB0; pBo[OB] = tB1; }
+            if (HAS_HI) { pB[ROWBUF] = uB0; pBo[ROWBUF + OB] = uB1; }
         }
     };
     // ring of RING stages (scalar arrays, fully unrolled: everything stays in registers), refilled in place; the list is padded to whole

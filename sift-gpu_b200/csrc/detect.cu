@@ -213,46 +213,21 @@ __global__ void __launch_bounds__(128) refine_kernel(const __grid_constant__ Pyr
 // on a Gaussian level.  Windows of neighbouring keypoints overlap and a frame has more window samples (~9 M) than level
 // pixels (2*sumP = 5.5 M), so the pair {Mag, Ori} is computed ONCE per pixel here -- same operations, bit-identical values --
 // and the two consumers gather one float2 per sample instead of four floats plus the atan2/sqrt arithmetic.
-// Warp = strip of 32 columns x GR_ROWS rows, 128-byte aligned (full-line loads and float2 stores).  All GR_ROWS+2 row loads of
-// a level are issued before any arithmetic (memory-level parallelism: the kernel is bandwidth/latency bound, not compute
-// bound); dx comes from two shuffles per row (the strip's left/right neighbours are fetched by lanes 0 and 31), dy from the
-// rows in registers.
-#ifndef GR_MIN_CTAS
-#define GR_MIN_CTAS 8
-#endif
-constexpr int GR_COLS = 32, GR_ROWS = kGradRows, GR_WARPS = 4;
+// Warp = strip of 64 columns x GR_ROWS rows of ONE level, 256-byte aligned; a lane owns two adjacent columns: one 8-byte load per
+// row, one 16-byte store per row ({Mag, Ori} of both pixels), and the horizontal neighbours of the pair come from two shuffles
+// (the strip's outer neighbours are fetched by lanes 0 and 31).  All row loads are issued before any arithmetic.  Pixels of the
+// first/last row and column get no meaningful value and are never sampled (0 < y < rows-1, 0 < x < cols-1 in both consumers);
+// the 16-byte store may cover such a pixel or the row padding.
+constexpr int GR_COLS = kGradCols, GR_ROWS = kGradRows, GR_WARPS = 4;
+static_assert(GR_COLS == 64, "two columns per lane");
 
-template <int NL>
-__device__ __forceinline__ void gradient_strip(const float* const (&G)[NL], float2* const (&MO)[NL], int rows, int cols, int pitch, int x, int y0, int y1,
-                                               int lane) {
-    const bool col_out = x >= 1 && x < cols - 1;
-    const int xc = x < cols ? x : cols - 1;
-    // halo column fetched by this lane (lane 0: x-1, lane 31: x+1), clamped into the row; other lanes never use it
-    const int xh = lane == 0 ? max(x - 1, 0) : min(x + 1, cols - 1);
-    const bool has_h = lane == 0 || lane == 31;
-#pragma unroll
-    for (int l = 0; l < NL; ++l) {
-        float v[GR_ROWS + 2], h[GR_ROWS];
-#pragma unroll
-        for (int k = 0; k < GR_ROWS + 2; ++k) v[k] = __ldg(G[l] + (size_t)min(y0 - 1 + k, rows - 1) * pitch + xc);
-#pragma unroll
-        for (int k = 0; k < GR_ROWS; ++k) h[k] = has_h ? __ldg(G[l] + (size_t)min(y0 + k, rows - 1) * pitch + xh) : 0.f;
-#pragma unroll
-        for (int k = 0; k < GR_ROWS; ++k) {
-            float right = __shfl_down_sync(0xffffffffu, v[k + 1], 1), left = __shfl_up_sync(0xffffffffu, v[k + 1], 1);
-            if (lane == 0) left = h[k];
-            if (lane == 31) right = h[k];
-            const float dx = right - left;
-            const float dy = v[k] - v[k + 2];
-            if (col_out && y0 + k < y1) MO[l][(size_t)(y0 + k) * pitch + x] = make_float2(sqrtf(dx * dx + dy * dy), fast_atan2_deg(dy, dx));
-        }
-    }
+__device__ __forceinline__ float2 grad_px(float left, float right, float up, float down) {
+    const float dx = right - left, dy = up - down;
+    return make_float2(sqrtf(dx * dx + dy * dy), fast_atan2_deg(dy, dx));
 }
 
-// FULL = false: levels 1,2 (the fused pipeline); FULL = true: all five levels (stage-level API).  Two kernels, so that the hot one is
-// register-allocated on its own (as one kernel with a run-time switch the two-level path spilled).
-template <bool FULL>
-__global__ void __launch_bounds__(GR_WARPS * 32, FULL ? 4 : GR_MIN_CTAS) gradient_kernel(const __grid_constant__ PyrView pv) {
+// levels lv0 + blockIdx.z: {1, 2} in the fused pipeline, all five in the stage-level API
+__global__ void __launch_bounds__(GR_WARPS * 32) gradient_kernel(const __grid_constant__ PyrView pv, int lv0) {
     const int lane = threadIdx.x & 31;
     const int strip = blockIdx.x * GR_WARPS + (threadIdx.x >> 5);
     if (strip >= pv.total_grad_tiles) return;
@@ -263,18 +238,34 @@ __global__ void __launch_bounds__(GR_WARPS * 32, FULL ? 4 : GR_MIN_CTAS) gradien
     const OctaveView& ov = pv.oct[o];
     const int t = strip - ov.grad_tile_base;
     const int rows = ov.rows, cols = ov.cols, pitch = ov.pitch;
-    const int x = (t % ov.grad_tiles_x) * GR_COLS + lane;
-    const int y0 = 1 + (t / ov.grad_tiles_x) * GR_ROWS;                     // only 0 < y < rows-1, 0 < x < cols-1 is ever sampled
+    const int x = (t % ov.grad_tiles_x) * GR_COLS + 2 * lane;
+    const int y0 = 1 + (t / ov.grad_tiles_x) * GR_ROWS;  // only 0 < y < rows-1, 0 < x < cols-1 is ever sampled
     const int y1 = min(y0 + GR_ROWS, rows - 1);
     const size_t foff = (size_t)blockIdx.y * ov.frame_stride;
-    if (!FULL) {
-        const float* const G[2] = {ov.G[1] + foff, ov.G[2] + foff};
-        float2* const MO[2] = {ov.MO[1] + foff, ov.MO[2] + foff};
-        gradient_strip<2>(G, MO, rows, cols, pitch, x, y0, y1, lane);
-    } else {
-        const float* const G[5] = {ov.G[0] + foff, ov.G[1] + foff, ov.G[2] + foff, ov.G[3] + foff, ov.G[4] + foff};
-        float2* const MO[5] = {ov.MO[0] + foff, ov.MO[1] + foff, ov.MO[2] + foff, ov.MO[3] + foff, ov.MO[4] + foff};
-        gradient_strip<5>(G, MO, rows, cols, pitch, x, y0, y1, lane);
+    const int level = lv0 + blockIdx.z;
+    const float* __restrict__ G = ov.G[level] + foff;
+    float2* __restrict__ MO = ov.MO[level] + foff;
+    const int xl = min(x, pitch - 2);  // loads stay inside the row (pitch is even); columns >= cols only feed pixels that are not stored
+    const int xh = lane == 0 ? max(x - 1, 0) : min(x + 2, pitch - 1);  // outer neighbour column of the strip (lanes 0 and 31)
+    const bool has_h = lane == 0 || lane == 31;
+    float2 v[GR_ROWS + 2];
+    float h[GR_ROWS];
+#pragma unroll
+    for (int k = 0; k < GR_ROWS + 2; ++k) v[k] = __ldg(reinterpret_cast<const float2*>(G + (size_t)min(y0 - 1 + k, rows - 1) * pitch + xl));
+#pragma unroll
+    for (int k = 0; k < GR_ROWS; ++k) h[k] = has_h ? __ldg(G + (size_t)min(y0 + k, rows - 1) * pitch + xh) : 0.f;
+    float4* out = reinterpret_cast<float4*>(MO + (size_t)y0 * pitch + x);
+    const bool col_ok = x < cols;
+#pragma unroll
+    for (int k = 0; k < GR_ROWS; ++k) {
+        const float2 c = v[k + 1];
+        float left = __shfl_up_sync(0xffffffffu, c.y, 1), right = __shfl_down_sync(0xffffffffu, c.x, 1);
+        if (lane == 0) left = h[k];
+        if (lane == 31) right = h[k];
+        const float2 p0 = grad_px(left, c.y, v[k].x, v[k + 2].x);
+        const float2 p1 = grad_px(c.x, right, v[k].y, v[k + 2].y);
+        if (col_ok && y0 + k < y1) *out = make_float4(p0.x, p0.y, p1.x, p1.y);
+        out += pitch / 2;
     }
 }
 
@@ -492,9 +483,9 @@ int launch_extrema(const PyrView& pv, const DetectBuf& db, int n_frames, cudaStr
 }
 
 int launch_gradient(const PyrView& pv, int n_frames, cudaStream_t st) {
-    const dim3 grid((pv.total_grad_tiles + GR_WARPS - 1) / GR_WARPS, n_frames);
-    if (pv.oct[0].MO[0] != nullptr) gradient_kernel<true><<<grid, GR_WARPS * 32, 0, st>>>(pv);
-    else gradient_kernel<false><<<grid, GR_WARPS * 32, 0, st>>>(pv);
+    const bool full = pv.oct[0].MO[0] != nullptr;
+    const dim3 grid((pv.total_grad_tiles + GR_WARPS - 1) / GR_WARPS, n_frames, full ? kNumScales : kOctaveLayers);
+    gradient_kernel<<<grid, GR_WARPS * 32, 0, st>>>(pv, full ? 0 : 1);
     return 1;
 }
 

@@ -25,7 +25,8 @@ constexpr int kMaxRadius = 18;     // floor(3*sig[4]) = floor(3*6.196774)
 #ifndef GR_ROWS_
 #define GR_ROWS_ 8
 #endif
-constexpr int kGradRows = GR_ROWS_; // rows of a gradient strip (32 aligned columns x kGradRows rows per warp, detect.cu)
+constexpr int kGradRows = GR_ROWS_; // rows of a gradient strip (kGradCols aligned columns x kGradRows rows per warp, detect.cu)
+constexpr int kGradCols = 64;
 
 struct OctaveView {
     float* G[kNumScales];     // Gaussian levels (G[3], G[4] may be null in the fused pipeline)
@@ -35,7 +36,7 @@ struct OctaveView {
     size_t frame_stride;      // floats between consecutive frames of one level
     int tile_base;            // first extrema strip (30x16 outputs) of this octave in the flattened strip index
     int tiles_x;
-    int grad_tile_base;       // first gradient strip (32x8 outputs) of this octave in the flattened strip index
+    int grad_tile_base;       // first gradient strip (kGradCols x kGradRows outputs) of this octave in the flattened strip index
     int grad_tiles_x;
 };
 
