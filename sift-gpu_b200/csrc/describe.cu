@@ -41,12 +41,13 @@ constexpr int NSLAB = DW + 1;  // floor(rbin) in -1..3
 //   DESC_CELLS 6: cells c0+1 in 0..5, cells 0 and 5 are scratch for the out-of-grid column votes (no extra instruction)
 //              5: one scratch cell (index 0) shared by c0 = -1 and c0+1 = 4 (one select)
 //              4: no scratch: out-of-grid votes are clamped into the grid and their stores predicated off
-//   DESC_BINS  9: bin o0+1 = 8 is folded onto bin 0 in the tail;  8: (o0+1) & 7 wraps at vote time
+//   DESC_BINS  9: bin o0+1 = 8 is folded onto bin 0 in the tail;  8: (o0+1) & 7 wraps at vote time (measured 41.3 vs 42.7 us/frame: the
+//              second column-sum pass for the folded bin goes away and a tenth CTA fits an SM)
 #ifndef DESC_CELLS
 #define DESC_CELLS 4
 #endif
 #ifndef DESC_BINS
-#define DESC_BINS 9
+#define DESC_BINS 8
 #endif
 constexpr int PC = DESC_CELLS;  // private cells per cell-row
 constexpr int PB = DESC_BINS;   // private bins per cell
