@@ -667,12 +667,12 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--frames", type=int, default=256, help="frames per GPU per step")
+    ap.add_argument("--frames", type=int, default=512, help="frames per GPU per step (one host-API call: its pipeline fill and drain are paid once per call)")
     ap.add_argument("--chunk", type=int, default=32, help="frames per internal pass (workspace size)")
     ap.add_argument("--cap", type=int, default=6144, help="keypoint capacity per frame")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="config2", choices=["config2", "config3", "config4", "config5"],
-                    help="config2: the headline (256 synthetic 1080p frames per GPU per step, weak scaling); config4: 1024 frames sharded 1024/G "
+                    help="config2: the headline (512 synthetic 1080p frames per GPU per step, weak scaling); config4: 1024 frames sharded 1024/G "
                          "(strong scaling); config3: 4K + 2x upsample; config5: query vs scene incl. matching")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true")

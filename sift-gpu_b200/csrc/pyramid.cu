@@ -46,8 +46,17 @@ void upload_taps(const float host_taps[5][kTapStride]) {
 namespace {
 
 constexpr int TW = 32;   // tile width  (= warp width: one lane per column in the vertical pass)
-constexpr int TH = 64;   // tile height
-constexpr int NT = 256;  // threads per CTA
+#ifndef TILE_H
+#define TILE_H 64
+#endif
+#ifndef OCT_CTAS
+#define OCT_CTAS 3
+#endif
+#ifndef BASE_CTAS
+#define BASE_CTAS 4
+#endif
+constexpr int TH = TILE_H;      // tile height
+constexpr int NT = TILE_H * 4;  // threads per CTA: one warp per 8 output rows in the vertical pass
 constexpr int GRP = 8;   // outputs per thread along the filter direction
 constexpr int HP2 = TW + 1;  // pitch of the horizontal-pass results, in float2 (odd)
 
@@ -221,7 +230,7 @@ struct OctArgs {
 // One CTA per tile, 3 CTAs per SM.  Two variants were measured slower and dropped (profiles/README.md): a persistent CTA that
 // kept the next tile's loads in flight in registers (128 registers -> 2 CTAs/SM, 46.7 us), and a CTA marching down four blocks
 // re-using the last 2R horizontal-pass rows (13 % fewer FFMAs but spills, an extra barrier and a row shift per block: 46 us).
-__global__ void __launch_bounds__(NT, 3) octave_kernel(const OctArgs a) {
+__global__ void __launch_bounds__(NT, OCT_CTAS) octave_kernel(const OctArgs a) {
     extern __shared__ float2 smem2[];
     float2* sIn = smem2;
     float2* sH = smem2 + OCT_IN;
@@ -311,7 +320,7 @@ constexpr int BASE_HALO = 4;
 constexpr int BASE_IN = (TW + 2 * BASE_HALO + 1) * (TH / 2 + BASE_HALO);
 constexpr int BASE_SMEM_BYTES = (BASE_IN + (TH / 2 + 4) * HP2) * 8;
 
-__global__ void __launch_bounds__(NT, 4)
+__global__ void __launch_bounds__(NT, BASE_CTAS)
     base_blur_kernel(const float* __restrict__ src, const uint8_t* __restrict__ src8, size_t src_frame_stride, int src_pitch, float* __restrict__ dst,
                      size_t dst_frame_stride, int dst_pitch, int rows, int cols, int vec) {
     extern __shared__ float2 smem2[];
