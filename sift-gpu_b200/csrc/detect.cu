@@ -12,9 +12,10 @@
 //                       survivors run the Taylor refinement + contrast/edge rejection inline and append a 32-byte
 //                       record through one atomic counter per frame.
 //   gradient_kernel     {magnitude, fastAtan2 orientation} of every pixel of G1/G2, once, for the two window consumers.
-//   orientation_kernel  warp per refined point; lanes stride over the window and vote into LANE-PRIVATE 36-bin
-//                       histograms in shared memory ([bin][lane], conflict-free plain adds: shared float atomics
-//                       are CAS loops on sm_100a), summed with a rotated read; shuffle max-reduce, peak split.
+//   orientation_kernel  warp per refined point; lane = window column, the warp walks down the window rows (batches of
+//                       four gathers, the next batch in flight) with a separable Gaussian weight, and votes into
+//                       LANE-PRIVATE 36-bin histograms in shared memory ([bin][lane], conflict-free plain adds: shared
+//                       float atomics are CAS loops on sm_100a), summed with rotated 16-byte reads; shuffle max, peak split.
 //   order_scan_kernel   CTA per frame: bitonic sort of (scan-order key, index) + exclusive scan of peak counts
 //                       => output slot of every (point, peak) in the reference's push_back order (:538).
 #include "sift_internal.cuh"
@@ -271,11 +272,18 @@ __global__ void __launch_bounds__(GR_WARPS * 32) gradient_kernel(const __grid_co
 
 // ---- orientation: calcOrientationHist + peak logic, src/sift.cpp:389-458, 518-541 ----------------------------
 constexpr int ORI_WARPS = 8;
+#ifndef ORI_BATCH_
+#define ORI_BATCH_ 4
+#endif
+constexpr int ORI_BATCH = ORI_BATCH_;  // window rows gathered per batch (two batches in flight)
 
-__global__ void __launch_bounds__(ORI_WARPS * 32) orientation_kernel(const __grid_constant__ PyrView pv, const DetectBuf db) {
+#ifndef ORI_MIN_CTAS
+#define ORI_MIN_CTAS 4
+#endif
+__global__ void __launch_bounds__(ORI_WARPS * 32, ORI_MIN_CTAS) orientation_kernel(const __grid_constant__ PyrView pv, const DetectBuf db) {
     __shared__ float s_tmp[ORI_WARPS][kOriBins + 4];
     __shared__ float s_hist[ORI_WARPS][kOriBins];
-    __shared__ float s_priv[ORI_WARPS][kOriBins * 32];  // lane-private bins, [bin][lane]
+    __shared__ __align__(16) float s_priv[ORI_WARPS][kOriBins * 32];  // lane-private bins, [bin][lane]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int f = blockIdx.y;
     int n = db.n_refined[f];
@@ -296,57 +304,57 @@ __global__ void __launch_bounds__(ORI_WARPS * 32) orientation_kernel(const __gri
         float* priv = s_priv[warp] + lane;
 #pragma unroll
         for (int b = 0; b < kOriBins; ++b) priv[b * 32] = 0.f;
-        // window (2*radius+1)^2 in raster order; rows/cols outside 0 < y < rows-1, 0 < x < cols-1 are skipped (:405,410)
-        const int w = 2 * radius + 1;
+        // window (2*radius+1)^2; rows/cols outside 0 < y < rows-1, 0 < x < cols-1 are skipped (:405,410).  Lane = window column (passes of 32
+        // columns; a pipeline window has at most 35), the warp walks down the rows: the address advances by the pitch, the column part of
+        // the weight is a per-lane constant and the row part is warp-uniform, so a sample costs a load, two multiplies, the bin and the
+        // lane-private add.  The Gaussian weight exp((i^2 + j^2) * s) is taken as exp(i^2 s) * exp(j^2 s) from one 32-entry table held
+        // across the lanes (radius < 32; a few ulp from the exp of the sum, far below what moves a peak); larger windows use the direct form.
         const int i_lo = max(-radius, 1 - py), i_hi = min(radius, rows - 2 - py);
         const int j_lo = max(-radius, 1 - px), j_hi = min(radius, cols - 2 - px);
-        const int wj = j_hi - j_lo + 1;
-        if (wj > 0 && i_lo <= i_hi) {
-            // flat raster index over the clipped window, 4 samples per lane per iteration: the four gradient-map loads are issued
-            // back to back (the kernel is bound by gather latency, not arithmetic); votes then go to the lane-private bins in order
-            const int total = (i_hi - i_lo + 1) * wj;
-            const float2* base = mo + (size_t)py * pitch + px;
-            int ci = i_lo + lane / wj, cj = j_lo + lane % wj;  // running (row, col) of this lane's next sample, advanced by 32 without divisions
-            // software pipeline: the four loads of batch k+1 are issued before the votes of batch k (ncu: with one batch in flight, 46 %
-            // of the kernel's stall samples sat on the first use of the gathered values)
-            struct Batch { int ii[4], jj[4]; float2 g[4]; };
-            auto fetch = [&](Batch& b, int idx0) {
+        const bool use_tab = radius < 32;
+        const float tab = expf((float)(lane * lane) * expf_scale);  // entry |k| = lane
+        if (i_lo <= i_hi) {
+            for (int cb = j_lo; cb <= j_hi; cb += 32) {
+                const int j = cb + lane;
+                const bool col_ok = j <= j_hi;
+                const int jc = col_ok ? j : j_hi;  // clamped: a readable pixel, its vote is dropped
+                const float wtab = __shfl_sync(0xffffffffu, tab, abs(jc) & 31);  // every lane takes part in the shuffle
+                const float wcol = !col_ok ? 0.f : use_tab ? wtab : 1.f;          // a clamped lane votes zeros
+                const float2* ptr = mo + (size_t)(py + i_lo) * pitch + (px + jc);
+                auto vote = [&](const float2 g, int ii) {
+                    const float wt = __shfl_sync(0xffffffffu, tab, abs(ii) & 31);
+                    const float wrow = use_tab ? wt : expf((float)(ii * ii + jc * jc) * expf_scale);
+                    int bin = cv_round((kOriBins / 360.f) * g.y);
+                    if (bin >= kOriBins) bin -= kOriBins;
+                    if (bin < 0) bin += kOriBins;
+                    priv[bin * 32] += (wrow * wcol) * g.x;
+                };
+                // batches of ORI_BATCH rows; the gathers of the next batch are issued before the votes of the current one
+                const int nrows_w = i_hi - i_lo + 1;
+                float2 cur[ORI_BATCH], nxt[ORI_BATCH];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    b.ii[u] = ci; b.jj[u] = cj;
-                    b.g[u] = make_float2(0.f, 0.f);
-                    if (idx0 + 32 * u < total) b.g[u] = __ldg(base + (ptrdiff_t)ci * pitch + cj);
-                    cj += 32;
-                    while (cj > j_hi) { cj -= wj; ++ci; }
-                }
-            };
-            auto vote = [&](const Batch& b, int idx0) {
+                for (int u = 0; u < ORI_BATCH; ++u) cur[u] = u < nrows_w ? __ldg(ptr + (size_t)u * pitch) : make_float2(0.f, 0.f);
+                for (int r0 = 0; r0 < nrows_w; r0 += ORI_BATCH) {
+                    ptr += (size_t)ORI_BATCH * pitch;
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    if (idx0 + 32 * u < total) {
-                        const float wgt = expf((b.ii[u] * b.ii[u] + b.jj[u] * b.jj[u]) * expf_scale);
-                        int bin = cv_round((kOriBins / 360.f) * b.g[u].y);
-                        if (bin >= kOriBins) bin -= kOriBins;
-                        if (bin < 0) bin += kOriBins;
-                        priv[bin * 32] += wgt * b.g[u].x;
-                    }
+                    for (int u = 0; u < ORI_BATCH; ++u) nxt[u] = r0 + ORI_BATCH + u < nrows_w ? __ldg(ptr + (size_t)u * pitch) : make_float2(0.f, 0.f);
+#pragma unroll
+                    for (int u = 0; u < ORI_BATCH; ++u)
+                        if (r0 + u < nrows_w) vote(cur[u], i_lo + r0 + u);
+#pragma unroll
+                    for (int u = 0; u < ORI_BATCH; ++u) cur[u] = nxt[u];
                 }
-            };
-            Batch b0, b1;
-            fetch(b0, lane);
-            for (int idx0 = lane; idx0 < total; idx0 += 256) {
-                fetch(b1, idx0 + 128);   // past the end: no loads, only index bookkeeping
-                vote(b0, idx0);
-                fetch(b0, idx0 + 256);
-                vote(b1, idx0 + 128);
             }
         }
-        (void)w;
         __syncwarp();
-        for (int b = lane; b < kOriBins; b += 32) {  // rotated read: lane b starts at copy b, all banks distinct
+        for (int b = lane; b < kOriBins; b += 32) {  // 16-byte reads of the bin's 32 copies, rotated by the lane: all banks distinct
+            const float* col = s_priv[warp] + b * 32;
             float acc = 0.f;
-#pragma unroll 8
-            for (int k = 0; k < 32; ++k) acc += s_priv[warp][b * 32 + ((k + b) & 31)];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const float4 t = *reinterpret_cast<const float4*>(col + (((q + lane) & 7) << 2));
+                acc += (t.x + t.y) + (t.z + t.w);
+            }
             temphist[b] = acc;
         }
         __syncwarp();
