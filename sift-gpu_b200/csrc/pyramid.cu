@@ -227,6 +227,25 @@ struct OctArgs {
     size_t nframe_stride;
 };
 
+#ifndef OCT_SPLIT_BARRIER
+#define OCT_SPLIT_BARRIER 1
+#endif
+// mbarrier helpers (one phase per CTA: a tile is processed once)
+__device__ __forceinline__ void bar_init(unsigned long long* b, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void warp_arrive(unsigned long long* b) {
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"((unsigned)__cvta_generic_to_shared(b)) : "memory");
+}
+__device__ __forceinline__ void bar_wait(unsigned long long* b) {
+    unsigned ok;
+    do {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.acquire.cta.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(ok) : "r"((unsigned)__cvta_generic_to_shared(b)) : "memory");
+    } while (!ok);
+}
+
 // One CTA per tile, 3 CTAs per SM.  Two variants were measured slower and dropped (profiles/README.md): a persistent CTA that
 // kept the next tile's loads in flight in registers (128 registers -> 2 CTAs/SM, 46.7 us), and a CTA marching down four blocks
 // re-using the last 2R horizontal-pass rows (13 % fewer FFMAs but spills, an extra barrier and a row shift per block: 46 us).
@@ -236,6 +255,13 @@ __global__ void __launch_bounds__(NT, OCT_CTAS) octave_kernel(const OctArgs a) {
     float2* sH = smem2 + OCT_IN;
     using IO = TileIO<OCT_HALO>;
     const int tid = threadIdx.x;
+#if OCT_SPLIT_BARRIER
+    __shared__ unsigned long long s_bar[4];
+    if (tid == 0) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) bar_init(&s_bar[q], NT / 32);
+    }
+#endif
     const int tx0 = blockIdx.x * TW, ty0 = blockIdx.y * TH;
     const int f = blockIdx.z;
     const size_t foff = (size_t)f * a.frame_stride;
@@ -245,18 +271,39 @@ __global__ void __launch_bounds__(NT, OCT_CTAS) octave_kernel(const OctArgs a) {
         IO::stash(pre, sIn, a.cols, tx0, tid);
     }
     __syncthreads();
+    const int x = tid & 31, rg = tid >> 5;
+    float g1[GRP], g2[GRP], g3[GRP], g4[GRP];
+#if OCT_SPLIT_BARRIER
+    // One mbarrier per scale instead of one CTA barrier between the passes: a warp signals each scale's horizontal results as it finishes
+    // them, and the vertical pass of scale 4 (done first by everybody) starts as soon as ITS rows are complete -- warps with fewer
+    // horizontal items no longer idle until the slowest warp has finished the last scale.
+    hpass<4, OCT_HALO>(sIn, sH + H_OFF4, tid);
+    warp_arrive(&s_bar[3]);
+    hpass<3, OCT_HALO>(sIn, sH + H_OFF3, tid);
+    warp_arrive(&s_bar[2]);
+    hpass<2, OCT_HALO>(sIn, sH + H_OFF2, tid);
+    warp_arrive(&s_bar[1]);
+    hpass<1, OCT_HALO>(sIn, sH + H_OFF1, tid);
+    warp_arrive(&s_bar[0]);
+    bar_wait(&s_bar[3]);
+    fir8_col<4>(sH + H_OFF4 + (rg * GRP / 2) * HP2 + x, g4);
+    bar_wait(&s_bar[2]);
+    fir8_col<3>(sH + H_OFF3 + (rg * GRP / 2) * HP2 + x, g3);
+    bar_wait(&s_bar[1]);
+    fir8_col<2>(sH + H_OFF2 + (rg * GRP / 2) * HP2 + x, g2);
+    bar_wait(&s_bar[0]);
+    fir8_col<1>(sH + H_OFF1 + (rg * GRP / 2) * HP2 + x, g1);
+#else
     hpass<4, OCT_HALO>(sIn, sH + H_OFF4, tid);
     hpass<3, OCT_HALO>(sIn, sH + H_OFF3, tid);
     hpass<2, OCT_HALO>(sIn, sH + H_OFF2, tid);
     hpass<1, OCT_HALO>(sIn, sH + H_OFF1, tid);
     __syncthreads();
-
-    const int x = tid & 31, rg = tid >> 5;
-    float g1[GRP], g2[GRP], g3[GRP], g4[GRP];
     fir8_col<1>(sH + H_OFF1 + (rg * GRP / 2) * HP2 + x, g1);
     fir8_col<2>(sH + H_OFF2 + (rg * GRP / 2) * HP2 + x, g2);
     fir8_col<3>(sH + H_OFF3 + (rg * GRP / 2) * HP2 + x, g3);
     fir8_col<4>(sH + H_OFF4 + (rg * GRP / 2) * HP2 + x, g4);
+#endif
 
     const int gx = tx0 + x;
     constexpr int IP2 = TW + 2 * OCT_HALO + 1;

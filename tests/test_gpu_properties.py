@@ -158,6 +158,15 @@ def test_edge_cases_and_errors(pkg, oracle, synth):
         s.cal_descriptor(g, big.shape[0], big.shape[1], bad)
     assert e.value.code == pkg.ERR_ASSERT
     assert s.cal_descriptor(g, big.shape[0], big.shape[1], full_k[:0]).shape == (0, 128)  # empty keypoint list
+    # caller-supplied keypoints whose window misses the image entirely (no sample passes 0 < r < rows-1, 0 < c < cols-1, :621): the
+    # reference leaves the histogram empty and returns an all-zero row; so does the oracle, so must the kernel (no stale shared memory)
+    off = full_k[:3].copy()
+    off["x"] = [-500.0, big.shape[1] + 400.0, 10.0]
+    off["y"] = [20.0, big.shape[0] + 300.0, -700.0]
+    got = s.cal_descriptor(g, big.shape[0], big.shape[1], np.concatenate([full_k[:5], off, full_k[5:9]]))
+    want = oracle.f32().cal_descriptor(g, big.shape[0], big.shape[1], np.concatenate([full_k[:5], off, full_k[5:9]]))
+    assert np.array_equal(got[5:8], np.zeros((3, 128), np.float32)) and np.array_equal(want[5:8], got[5:8])
+    assert (np.linalg.norm(got - want, axis=1) <= 1e-3).mean() >= 0.8  # the in-image rows around them are untouched by the empty ones
     s.close()
 
 
