@@ -118,9 +118,9 @@ int make_view(float* base, int rows, int cols, int n_oct, int n_frames, bool ful
         gtiles += (cols > 2 && rows > 2) ? v.grad_tiles_x * ((rows - 2 + kGradRows - 1) / kGradRows) : 0;
         // extrema strips: 30 x 16 outputs over the interior [5, rows-5) x [5, cols-5)  (detect.cu)
         const int in_c = cols - 2 * kImgBorder, in_r = rows - 2 * kImgBorder;
-        v.tiles_x = in_c > 0 ? (in_c + 29) / 30 : 0;
+        v.tiles_x = in_c > 0 ? (in_c + kExtremaCols - 1) / kExtremaCols : 0;
         v.tile_base = tiles;
-        tiles += (in_c > 0 && in_r > 0) ? v.tiles_x * ((in_r + 15) / 16) : 0;
+        tiles += (in_c > 0 && in_r > 0) ? v.tiles_x * ((in_r + kExtremaRows - 1) / kExtremaRows) : 0;
         rows /= 2; cols /= 2;
     }
     pv->total_tiles = tiles;

@@ -5,7 +5,7 @@
 // reference's expression order, so that given identical DoG/Gaussian levels the refinement arithmetic
 // matches the CPU bit for bit (only expf/exp2 differ by library).
 //
-//   extrema_kernel      warp = 30 columns x 16 rows strip (+1 halo lane each side, +1 halo row above/below).  Per row
+//   extrema_kernel      warp = 30 columns x 64 rows strip (+1 halo lane each side, +1 halo row above/below).  Per row
 //                       the four DoG levels are loaded once (coalesced), the 3-wide row max/min come from two
 //                       shuffles, the 3-row column max/min from rolling registers: "val >= all 26 neighbours"
 //                       (:493-511) becomes val >= max of three 3x3 maxima, with no divergent probing.  The rare
@@ -116,8 +116,8 @@ __device__ bool adjust_local_extrema(const float* const* D, int rows, int cols, 
     return true;
 }
 
-constexpr int EX_COLS = 30;  // output columns per warp (lanes 1..30; lanes 0 and 31 are halo)
-constexpr int EX_ROWS = 16;  // output rows per warp
+constexpr int EX_COLS = kExtremaCols;  // output columns per warp (lanes 1..30; lanes 0 and 31 are halo)
+constexpr int EX_ROWS = kExtremaRows;  // output rows per warp
 constexpr int EX_WARPS = 4;
 
 __global__ void __launch_bounds__(EX_WARPS * 32) extrema_kernel(const __grid_constant__ PyrView pv, const DetectBuf db) {

@@ -27,6 +27,11 @@ constexpr int kMaxRadius = 18;     // floor(3*sig[4]) = floor(3*6.196774)
 #endif
 constexpr int kGradRows = GR_ROWS_; // rows of a gradient strip (kGradCols aligned columns x kGradRows rows per warp, detect.cu)
 constexpr int kGradCols = 64;
+#ifndef EX_ROWS_
+#define EX_ROWS_ 64
+#endif
+constexpr int kExtremaRows = EX_ROWS_;  // output rows of an extrema strip (30 output columns x kExtremaRows rows per warp, detect.cu)
+constexpr int kExtremaCols = 30;
 
 struct OctaveView {
     float* G[kNumScales];     // Gaussian levels (G[3], G[4] may be null in the fused pipeline)
