@@ -170,6 +170,43 @@ def test_edge_cases_and_errors(pkg, oracle, synth):
     s.close()
 
 
+def test_two_host_threads_two_handles(pkg, synth):
+    """The threading contract of include/sift_b200.h: different handles are independent, so two host threads, each driving its own handle
+    on its own half of a batch (what bench.py's e2e does), must return exactly what one call over the whole batch returns."""
+    import threading
+
+    frames = np.stack([synth.recipe_s(480, 270, seed=300 + k) for k in range(12)])
+    cap = 2048
+    one = pkg.Sift(270, 480, max_batch=2, max_kp_per_frame=cap)
+    w_kp = np.zeros((12, cap), dtype=pkg.KP_DTYPE); w_desc = np.zeros((12, cap, 128), dtype=np.float32); w_cnt = np.zeros(12, dtype=np.int32)
+    assert one.detect_describe_batch_host(frames, w_kp, w_desc, w_cnt, cap) == pkg.OK
+    one.close()
+    assert w_cnt.min() > 20
+    handles = [pkg.Sift(270, 480, max_batch=2, max_kp_per_frame=cap) for _ in range(2)]
+    g_kp = np.zeros_like(w_kp); g_desc = np.zeros_like(w_desc); g_cnt = np.zeros_like(w_cnt)
+    errs = []
+
+    def run(h, lo, hi):
+        try:
+            for _ in range(3):  # repeated calls: the two pipelines drift against each other
+                assert h.detect_describe_batch_host(frames[lo:hi], g_kp[lo:hi], g_desc[lo:hi], g_cnt[lo:hi], cap) == pkg.OK
+        except Exception as e:  # noqa: BLE001
+            errs.append(e)
+
+    th = [threading.Thread(target=run, args=(handles[0], 0, 6)), threading.Thread(target=run, args=(handles[1], 6, 12))]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    for h in handles:
+        h.close()
+    assert not errs, errs
+    assert np.array_equal(g_cnt, w_cnt)
+    for f in range(12):
+        assert g_kp[f, : w_cnt[f]].tobytes() == w_kp[f, : w_cnt[f]].tobytes()
+        assert np.array_equal(g_desc[f, : w_cnt[f]], w_desc[f, : w_cnt[f]])
+
+
 def test_internal_list_overflow_contract(pkg, synth):
     """A frame with more refined extrema than the handle's max_kp_per_frame: the true keypoint count is unknown, so the call reports
     max_kp + 1 with ERR_CAPACITY, writes only the records the kernels produced (all of them valid, in reference order) and leaves the
