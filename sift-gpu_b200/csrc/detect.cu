@@ -6,11 +6,12 @@
 // matches the CPU bit for bit (only expf/exp2 differ by library).
 //
 //   extrema_kernel      warp = 30 columns x 64 rows strip (+1 halo lane each side, +1 halo row above/below).  Per row
-//                       the four DoG levels are loaded once (coalesced), the 3-wide row max/min come from two
-//                       shuffles, the 3-row column max/min from rolling registers: "val >= all 26 neighbours"
-//                       (:493-511) becomes val >= max of three 3x3 maxima, with no divergent probing.  The rare
-//                       survivors run the Taylor refinement + contrast/edge rejection inline and append a 32-byte
-//                       record through one atomic counter per frame.
+//                       the four DoG levels are loaded once (coalesced); a lane keeps the two previous rows of its column,
+//                       so the max/min over the 3 rows x 3 levels of its own column are register operations, and the
+//                       neighbouring columns are consulted (four shuffles) only when some lane of the warp is the
+//                       extremum of its column neighbourhood beyond the threshold: "val >= all 26 neighbours" (:493-511)
+//                       without divergent probing.  Survivors are appended as 32-bit scan-order keys (the compiler
+//                       aggregates the atomic per warp); refine_kernel runs the Taylor refinement on them.
 //   gradient_kernel     {magnitude, fastAtan2 orientation} of every pixel of G1/G2, once, for the two window consumers.
 //   orientation_kernel  warp per refined point; lane = window column, the warp walks down the window rows (batches of
 //                       four gathers, the next batch in flight) with a separable Gaussian weight, and votes into
@@ -143,38 +144,39 @@ __global__ void __launch_bounds__(EX_WARPS * 32) extrema_kernel(const __grid_con
     const float* p2 = ov.D[2] + foff + (size_t)(r_begin - 1) * pitch + (col_in ? c : 0);
     const float* p3 = ov.D[3] + foff + (size_t)(r_begin - 1) * pitch + (col_in ? c : 0);
 
-    float hmaxA[4], hminA[4], hmaxB[4], hminB[4], cenB[2];
+    // Column first: the lane keeps the two previous rows of its column (raw values, four levels); per row the max/min over the three rows
+    // of each level and then over the three levels of a layer are plain register operations.  Only a pixel that is the extremum of its
+    // own column neighbourhood (9 values) can be one of all 27, so the neighbouring columns are consulted -- four shuffles -- only for
+    // (row, layer) pairs where some lane of the warp passes that filter and the |val| > 8 test; about half of them on the benchmark frames.
+    float ra[4], rb[4];  // rows y-2, y-1
 #pragma unroll
-    for (int l = 0; l < 4; ++l) { hmaxA[l] = hmaxB[l] = -3.4e38f; hminA[l] = hminB[l] = 3.4e38f; }
-    cenB[0] = cenB[1] = 0.f;
+    for (int l = 0; l < 4; ++l) ra[l] = rb[l] = 0.f;
     float nx[4] = {__ldg(p0), __ldg(p1), __ldg(p2), __ldg(p3)};  // row r_begin-1
 #pragma unroll 1
     for (int y = r_begin - 1; y <= r_end; ++y) {
-        float v[4] = {nx[0], nx[1], nx[2], nx[3]};
+        const float v[4] = {nx[0], nx[1], nx[2], nx[3]};
         if (y < r_end) {  // prefetch row y+1 (<= rows-5) while row y is processed
             p0 += pitch; p1 += pitch; p2 += pitch; p3 += pitch;
             nx[0] = __ldg(p0); nx[1] = __ldg(p1); nx[2] = __ldg(p2); nx[3] = __ldg(p3);
         }
-        float hmaxC[4], hminC[4];
-#pragma unroll
-        for (int l = 0; l < 4; ++l) {
-            const float vl = __shfl_up_sync(0xffffffffu, v[l], 1), vr = __shfl_down_sync(0xffffffffu, v[l], 1);
-            hmaxC[l] = fmaxf(v[l], fmaxf(vl, vr));
-            hminC[l] = fminf(v[l], fminf(vl, vr));
-        }
-        if (y >= r_begin + 1) {  // rows y-2, y-1, y are in flight: test row y-1
-            float M[4], m[4];
+        if (y >= r_begin + 1) {  // rows y-2, y-1, y are in registers: test row y-1
+            float cmx[4], cmn[4];
 #pragma unroll
             for (int l = 0; l < 4; ++l) {
-                M[l] = fmaxf(hmaxA[l], fmaxf(hmaxB[l], hmaxC[l]));
-                m[l] = fminf(hminA[l], fminf(hminB[l], hminC[l]));
+                cmx[l] = fmaxf(ra[l], fmaxf(rb[l], v[l]));
+                cmn[l] = fminf(ra[l], fminf(rb[l], v[l]));
             }
 #pragma unroll
             for (int layer0 = 1; layer0 <= kOctaveLayers; ++layer0) {
-                const float val = cenB[layer0 - 1];
+                const float val = rb[layer0];
+                const float A = fmaxf(cmx[layer0 - 1], fmaxf(cmx[layer0], cmx[layer0 + 1]));
+                const float B = fminf(cmn[layer0 - 1], fminf(cmn[layer0], cmn[layer0 + 1]));
                 // |val| > 8 (the literal threshold, :564) and val >= / <= all 26 neighbours (non-strict, :494-511)
-                const bool hit = col_out && ((val > 8.0f && val >= fmaxf(M[layer0 - 1], fmaxf(M[layer0], M[layer0 + 1]))) ||
-                                             (val < -8.0f && val <= fminf(m[layer0 - 1], fminf(m[layer0], m[layer0 + 1]))));
+                const bool own = col_out && ((val > 8.0f && val >= A) || (val < -8.0f && val <= B));
+                if (!__any_sync(0xffffffffu, own)) continue;
+                const float Al = __shfl_up_sync(0xffffffffu, A, 1), Ar = __shfl_down_sync(0xffffffffu, A, 1);
+                const float Bl = __shfl_up_sync(0xffffffffu, B, 1), Br = __shfl_down_sync(0xffffffffu, B, 1);
+                const bool hit = own && ((val > 8.0f && val >= fmaxf(Al, Ar)) || (val < -8.0f && val <= fminf(Bl, Br)));
                 if (hit) {
                     const int slot = atomicAdd(db.n_cand + f, 1);
                     if (slot < db.cap_c)
@@ -183,8 +185,7 @@ __global__ void __launch_bounds__(EX_WARPS * 32) extrema_kernel(const __grid_con
             }
         }
 #pragma unroll
-        for (int l = 0; l < 4; ++l) { hmaxA[l] = hmaxB[l]; hminA[l] = hminB[l]; hmaxB[l] = hmaxC[l]; hminB[l] = hminC[l]; }
-        cenB[0] = v[1]; cenB[1] = v[2];
+        for (int l = 0; l < 4; ++l) { ra[l] = rb[l]; rb[l] = v[l]; }
     }
 }
 
