@@ -121,7 +121,10 @@ constexpr int EX_COLS = kExtremaCols;  // output columns per warp (lanes 1..30; 
 constexpr int EX_ROWS = kExtremaRows;  // output rows per warp
 constexpr int EX_WARPS = 4;
 
-__global__ void __launch_bounds__(EX_WARPS * 32) extrema_kernel(const __grid_constant__ PyrView pv, const DetectBuf db) {
+#ifndef EX_MIN_CTAS
+#define EX_MIN_CTAS 1
+#endif
+__global__ void __launch_bounds__(EX_WARPS * 32, EX_MIN_CTAS) extrema_kernel(const __grid_constant__ PyrView pv, const DetectBuf db) {
     const int lane = threadIdx.x & 31;
     const int strip = blockIdx.x * EX_WARPS + (threadIdx.x >> 5);
     if (strip >= pv.total_tiles) return;
