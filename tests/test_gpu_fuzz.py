@@ -17,7 +17,13 @@ def _shapes():
     rng = np.random.default_rng(20261018)
     rnd = [(int(rng.integers(20, 420)), int(rng.integers(20, 520))) for _ in range(26)]
     big = [(int(rng.integers(600, 1100)), int(rng.integers(700, 1400))) for _ in range(4)]
-    return EDGE + rnd + big
+    # SIFT_FUZZ_EXTRA=N adds N more random shapes from another seed (a longer one-off sweep after kernel changes; not part of the default run)
+    import os
+
+    extra = int(os.environ.get("SIFT_FUZZ_EXTRA", "0"))
+    rng2 = np.random.default_rng(977)
+    more = [(int(rng2.integers(16, 700)), int(rng2.integers(16, 900))) for _ in range(extra)]
+    return EDGE + rnd + big + more
 
 
 @pytest.mark.parametrize("shape", _shapes(), ids=lambda s: f"{s[0]}x{s[1]}")
