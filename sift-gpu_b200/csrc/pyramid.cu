@@ -144,6 +144,30 @@ __device__ __forceinline__ void load_tile(float* __restrict__ sIn, const float* 
     }
 }
 
+// Masked tile load for a uint8 source whose rows are 4-byte aligned (cols, pitch and the tile origin multiples of 4): a thread takes
+// four columns of BOTH rows of a row pair -- two 4-byte loads, consecutive threads on consecutive quads of a row: coalesced -- and writes
+// four complete float2 {row 2p, row 2p+1} entries.  Same mask as load_tile (zero padding, last row / last column read as zero); the
+// byte-per-thread form costs twice the float path's time on the u8 front end of the host pipeline.
+template <int HALO>
+__device__ __forceinline__ void load_tile_u8x4(float2* __restrict__ sIn, const uint8_t* __restrict__ src8, int rows, int cols, int pitch, int ty0,
+                                               int tx0, int tid) {
+    constexpr int IW = TW + 2 * HALO, IH = TH + 2 * HALO, IP2 = IW + 1, NQ = IW / 4, NP = IH / 2;
+    static_assert(IW % 4 == 0 && HALO % 4 == 0 && IH % 2 == 0, "quads of columns, pairs of rows");
+    for (int id = tid; id < NP * NQ; id += NT) {
+        const int p = id / NQ, q = id - p * NQ;
+        const int gy = ty0 - HALO + 2 * p, gx = tx0 - HALO + 4 * q;
+        const bool col_in = gx >= 0 && gx < cols;  // a quad is inside the image as a whole
+        const uint8_t* ptr = src8 + (ptrdiff_t)gy * pitch + gx;
+        uint32_t a = 0u, b = 0u;
+        if (col_in && gy >= 0 && gy < rows - 1) a = __ldg(reinterpret_cast<const uint32_t*>(ptr));
+        if (col_in && gy + 1 >= 0 && gy + 1 < rows - 1) b = __ldg(reinterpret_cast<const uint32_t*>(ptr + pitch));
+        if (gx + 3 == cols - 1) { a &= 0x00ffffffu; b &= 0x00ffffffu; }  // the last column reads as zero (src/sift.cpp:116)
+        float2* dst = sIn + p * IP2 + 4 * q;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) dst[k] = make_float2((float)((a >> (8 * k)) & 255u), (float)((b >> (8 * k)) & 255u));
+    }
+}
+
 // Masked tile load for a float source with even pitch and even tile origin, in two halves (global loads first, shared stores
 // after).  Warp w owns row pairs w, w+8, ...; lane l owns column pair l (a thread reads the same two columns of BOTH rows of a
 // pair: two 8-byte loads, coalesced along the row) -- so the column mask is computed once per thread, the row mask is warp
@@ -376,7 +400,9 @@ __global__ void __launch_bounds__(NT, BASE_CTAS)
     float* sInF = reinterpret_cast<float*>(sIn);
     const int tid = threadIdx.x;
     const int tx0 = blockIdx.x * TW, ty0 = blockIdx.y * TH;
-    if (vec) {  // float source, aligned rows: 8-byte loads of row pairs
+    if (vec == 2) {  // uint8 source, 4-byte aligned rows
+        load_tile_u8x4<BASE_HALO>(sIn, src8 + (size_t)blockIdx.z * src_frame_stride, rows, cols, src_pitch, ty0, tx0, tid);
+    } else if (vec) {  // float source, aligned rows: 8-byte loads of row pairs
         using IO = TileIO<BASE_HALO>;
         float2 pre[2 * IO::NSLOT];
         IO::fetch(pre, src + (size_t)blockIdx.z * src_frame_stride, rows, src_pitch, ty0, tx0, tid);
@@ -472,7 +498,8 @@ void init_pyramid_kernels() {
 
 int launch_base_blur(const float* src, size_t src_frame_stride, int src_pitch, const uint8_t* src_u8, const OctaveView& o0, int n_frames, cudaStream_t st) {
     dim3 grid((o0.cols + TW - 1) / TW, (o0.rows + TH - 1) / TH, n_frames);
-    const int vec = !src_u8 && src_pitch % 4 == 0 && src_frame_stride % 4 == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0;
+    const int vec = src_u8 ? ((o0.cols % 4 == 0 && src_pitch % 4 == 0 && src_frame_stride % 4 == 0 && (reinterpret_cast<uintptr_t>(src_u8) & 3) == 0) ? 2 : 0)
+                           : (src_pitch % 4 == 0 && src_frame_stride % 4 == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0);
     base_blur_kernel<<<grid, NT, BASE_SMEM_BYTES, st>>>(src_u8 ? nullptr : src, src_u8, src_frame_stride, src_pitch, o0.G[0], o0.frame_stride, o0.pitch, o0.rows,
                                                        o0.cols, vec);
     return 1;
