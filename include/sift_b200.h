@@ -61,7 +61,7 @@ const char* sift_b200_version(void);
  * max_kp_per_frame keypoints per frame.  device = CUDA ordinal.
  * Threading: a handle serves one call at a time; different handles are independent (sift_b200_last_error is per thread).  A streaming
  * caller keeps a device busy with two host threads, one handle each, on alternate batches: one call's pipeline fill and drain then run
- * under the other's steady state (bench.py's e2e: 9.0 k frames/s against 8.5 k from one thread). */
+ * under the other's steady state (bench.py's e2e: 9.3 k frames/s against 8.95 k from one thread). */
 int sift_b200_create(SiftB200** out, int max_rows, int max_cols, int max_batch, int max_kp_per_frame, int device);
 int sift_b200_destroy(SiftB200* h);
 
