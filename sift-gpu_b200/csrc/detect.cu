@@ -502,7 +502,13 @@ int launch_gradient(const PyrView& pv, int n_frames, cudaStream_t st) {
 }
 
 int launch_orientation(const PyrView& pv, const DetectBuf& db, int n_frames, cudaStream_t st) {
-    dim3 grid(64, n_frames);
+    // whole waves: about 64 CTAs per frame, rounded so that the launch is a multiple of the CTAs the device holds at once (the last,
+    // partly filled wave of a 64 x 32 launch was 14 % of the kernel)
+    static int g_ori_ctas = getenv("SIFT_B200_ORI_CTAS") ? atoi(getenv("SIFT_B200_ORI_CTAS")) : 0;
+    const int resident = num_sms() * ORI_MIN_CTAS;
+    const int waves = (64 * n_frames + resident - 1) / resident;
+    const int per_frame = g_ori_ctas > 0 ? g_ori_ctas : (waves * resident + n_frames - 1) / n_frames;
+    dim3 grid(per_frame, n_frames);
     orientation_kernel<<<grid, ORI_WARPS * 32, 0, st>>>(pv, db);
     return 1;
 }
