@@ -319,12 +319,12 @@ __device__ void calc_descriptor(const float2* __restrict__ mo, int pitch, const 
                     int excl = 0;
 #pragma unroll
                     for (int bit = 0; bit < 5; ++bit) excl += __popc(__ballot_sync(0xffffffffu, (cnt >> bit) & 1) & lt_mask) << bit;
-                    const int base = total + excl - pass0;
-                    for (int c = 0; c < cnt; ++c) {
-                        const int idx = base + c;
-                        if (idx >= 0 && idx < NCHUNK)
-                            s_chunk[idx] = r | ((jlo + 4 * c - cb0) << 8) | (min(4, jhi - jlo - 4 * c + 1) << 16);
-                    }
+                    // whole 4-pixel chunks (the code advances by four columns per chunk), then the row's last chunk with what is left
+                    int idx = total + excl - pass0;
+                    int code = r | ((jlo - cb0) << 8) | (4 << 16);
+                    for (int c = 1; c < cnt; ++c, ++idx, code += 4 << 8)
+                        if ((unsigned)idx < (unsigned)NCHUNK) s_chunk[idx] = code;
+                    if (cnt > 0 && (unsigned)idx < (unsigned)NCHUNK) s_chunk[idx] = (code & 0xffff) | ((jhi - jlo - 4 * (cnt - 1) + 1) << 16);
                     total += __shfl_sync(0xffffffffu, excl + cnt, 31);
                 }
                 const int nchunks = min(NCHUNK, total - pass0);
